@@ -1,0 +1,171 @@
+/* rnamsm_b200 -- C ABI of the B200-native RNA-MSM forward path.
+ *
+ * Drop-in boundary.  The reference (yikunpku/RNA-MSM) is pure Python/PyTorch and has no FFI of
+ * its own: the boundary it exposes for this path is the nn.Module API
+ *   MSATransformer.forward(tokens, repr_layers, need_head_weights, return_contacts)  model.py:338-416
+ *   AxialTransformerLayer.forward(x, self_attn_mask, self_attn_padding_mask, need_head_weights)
+ *                                                                              modules.py:242-267
+ *   RowSelfAttention.forward / ColumnSelfAttention.forward                     modules.py:802-821, 926-945
+ *   FeedForwardNetwork.forward                                                 modules.py:423-427
+ * plus the state-dict names and the two .npy outputs (RNA_MSM_Inference.py:150-166).
+ * The Python package `rnamsm_b200` mirrors those classes one-for-one and binds the entry points
+ * below with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless named host_*;
+ *   - no allocation inside: the caller (PyTorch) owns inputs, outputs and workspaces;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
+ *   - return value 0 = ok; non-zero = error, message in rnamsm_last_error() (thread-local);
+ *   - `dtype` selects the arithmetic path: RNAMSM_F32 = fp32 FFMA kernels (parity path,
+ *     <=1e-4 norm-relative vs the reference fp32 forward), RNAMSM_BF16 = bf16 operands on the
+ *     tcgen05 tensor cores with fp32 accumulation, fp32 residual stream / LayerNorm / softmax
+ *     (<=2e-2).  There is no CPU fallback.
+ *   - one MSA per call (B = 1): the reference never batches MSAs (RNA_MSM_Inference.py:147)
+ *     and its tied-attention scaling depends on the padded row count (modules.py:713-715).
+ *   - activations are token-major: x[(r*C + c)*D + f], i.e. the reference's [R,C,B=1,D].
+ */
+#ifndef RNAMSM_B200_H_
+#define RNAMSM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNAMSM_ABI_VERSION 1
+
+enum { RNAMSM_F32 = 0, RNAMSM_BF16 = 1 };
+
+/* Epilogues of rnamsm_linear. */
+enum {
+  RNAMSM_EPI_BIAS = 0,          /* out = x W^T + b          (out in compute dtype)                 */
+  RNAMSM_EPI_BIAS_GELU = 1,     /* out = gelu_erf(x W^T + b)  nn.GELU(), modules.py:416,424        */
+  RNAMSM_EPI_BIAS_RESIDUAL = 2  /* out(fp32) += x W^T + b     NormalizedResidualBlock, modules.py:397 */
+};
+
+int rnamsm_version(void);
+const char* rnamsm_last_error(void);
+/* 0 when the current device is a compute-capability 10.x part (B200); error otherwise. */
+int rnamsm_device_check(void);
+/* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
+long long rnamsm_launch_count(void);
+
+/* K1 -- token + learned-position + per-row scalar embedding, LayerNorm, pad zeroing.
+ * Replaces model.py:346-367 and LearnedPositionalEmbedding.forward (modules.py:286-300).
+ * tokens [R,C] int64; tok_emb [vocab,D]; pos_emb [n_pos,D]; row_pos [>=R] scalars or NULL;
+ * x_out [R*C, D] fp32; pad_out [R*C] uint8 (1 where token == pad_idx) or NULL. */
+int rnamsm_embed_layernorm(const int64_t* tokens, int R, int C, const float* tok_emb, int vocab,
+                           const float* pos_emb, int n_pos, const float* row_pos, const float* ln_w,
+                           const float* ln_b, int D, int pad_idx, float eps, float* x_out,
+                           uint8_t* pad_out, void* stream);
+
+/* K2 / K9 -- LayerNorm over the last dim (nn.LayerNorm(D), biased variance), fp32 in,
+ * fp32 or bf16 out (modules.py:382,387; model.py:331-332,396). */
+int rnamsm_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows,
+                     int D, float eps, void* stream);
+
+/* K3 / K6-out / K8 -- nn.Linear with fused epilogue: out = epi(x[M,K] W[N,K]^T + bias[N]).
+ * x, W in `dtype`.  For RNAMSM_EPI_BIAS: columns [0,q_cols) are multiplied by q_scale after the
+ * bias (q *= scaling, modules.py:766, 905) and, when row_mask != NULL, by (1 - row_mask[m])
+ * (padded query rows zeroed, modules.py:767-772).  `out` is in `dtype` except for
+ * RNAMSM_EPI_BIAS_RESIDUAL where it is the fp32 residual stream updated in place. */
+int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, int N, int K, int dtype,
+                  int epilogue, float q_scale, int q_cols, const uint8_t* row_mask, void* out, void* stream);
+
+/* K4 -- tied row-attention logits (modules.py:774): for every head h
+ *   partial[s][h][i][j] = sum_{r in split s} sum_d q[r,i,h,d] k[r,j,h,d]
+ * qkv [R*C, 3*H*64] in `dtype`, q|k|v packed along the feature dim, q already scaled.
+ * partial: fp32 [n_splits, H, C, C].  n_splits >= 1 row ranges are summed by K5. */
+int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, float* partial, int n_splits,
+                           void* stream);
+/* Suggested split count for K4 so that the launch fills the 148 SMs. */
+int rnamsm_row_attn_splits(int R, int C, int H, int dtype);
+
+/* K5 -- sum the split partials, mask keys (logit = -10000 where key_pad[j], modules.py:780-784),
+ * softmax over j (modules.py:818).  probs_out fp32 [H,C,C] is the exported attention map
+ * (written straight into the caller's [N,H,C,C] slab); probs_lp ([H,C,ld_lp] in `dtype`, columns
+ * >= C zero-filled) feeds K6 and may be NULL in fp32 mode where K6 reads probs_out. */
+int rnamsm_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad,
+                       float* probs_out, void* probs_lp, int ld_lp, int dtype, void* stream);
+
+/* K6 -- ctx[r,i,h,:] = sum_j P[h,i,j] v[r,j,h,:] (modules.py:797).  probs [H,C,ldp] in `dtype`;
+ * ctx [R*C, H*64] in `dtype`. */
+int rnamsm_row_attn_av(const void* probs, int ldp, const void* qkv, int R, int C, int H, int dtype, void* ctx,
+                       void* stream);
+
+/* K7 -- column attention over the MSA depth, flash-style (modules.py:896-923): for every column c
+ * and head h, ctx[i,c,h,:] = softmax_j(q[i,c,h,:].k[j,c,h,:]) v[j,c,h,:]; q already scaled by
+ * 64^-0.5; keys with pad[j*C+c] != 0 get logit -10000 (modules.py:911-915).  R >= 2 (the R == 1
+ * shortcut of modules.py:882-894 is handled by the caller as out_proj(v_proj(x))). */
+int rnamsm_col_attn(const void* qkv, int R, int C, int H, int dtype, const uint8_t* pad, void* ctx, void* stream);
+
+/* K9b -- tied LM-head projection logits[m, v] = h[m,:] . E[v,:] + bias[v] (modules.py:318), fp32. */
+int rnamsm_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
+                      void* stream);
+
+/* ---- whole-layer / whole-model drivers (same kernels, one call) ------------------------------ */
+
+typedef struct rnamsm_attn_weights {
+  const float* ln_w; /* [D] pre-LN of the NormalizedResidualBlock */
+  const float* ln_b;
+  const void* w_qkv; /* [3D, D] rows = q_proj | k_proj | v_proj, compute dtype */
+  const float* b_qkv; /* [3D] */
+  const void* w_out; /* [D, D] compute dtype */
+  const float* b_out; /* [D] */
+} rnamsm_attn_weights;
+
+typedef struct rnamsm_layer_weights {
+  rnamsm_attn_weights row; /* layers.{l}.row_self_attention.*    */
+  rnamsm_attn_weights col; /* layers.{l}.column_self_attention.* */
+  const float* ffn_ln_w;
+  const float* ffn_ln_b;
+  const void* fc1_w; /* [F, D] */
+  const float* fc1_b;
+  const void* fc2_w; /* [D, F] */
+  const float* fc2_b;
+} rnamsm_layer_weights;
+
+typedef struct rnamsm_model_weights {
+  int num_layers, embed_dim, num_heads, ffn_dim, vocab, n_pos, pad_idx;
+  float ln_eps;
+  const float* tok_emb;  /* embed_tokens.weight [vocab, D] */
+  const float* pos_emb;  /* embed_positions.weight [n_pos, D] */
+  const float* row_pos;  /* msa_position_embedding flattened [1024] or NULL */
+  const float* ln_before_w;
+  const float* ln_before_b;
+  const float* ln_after_w;
+  const float* ln_after_b;
+  const float* lm_dense_w; /* [D, D] fp32 (the LM head always runs in fp32) */
+  const float* lm_dense_b;
+  const float* lm_ln_w;
+  const float* lm_ln_b;
+  const float* lm_bias;   /* [vocab] */
+  const rnamsm_layer_weights* layers; /* host array, num_layers entries */
+} rnamsm_model_weights;
+
+/* Bytes of scratch rnamsm_layer_forward / rnamsm_msa_forward need for an R x C MSA. */
+size_t rnamsm_workspace_bytes(int R, int C, int D, int H, int F, int dtype);
+
+/* One AxialTransformerLayer (modules.py:242-267) in place on x [R*C, D] fp32.
+ * pad [R*C] uint8 or NULL.  row_probs_out [H,C,C] fp32 or NULL (then a scratch map is used). */
+int rnamsm_layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, float ln_eps, float* x, int R, int C,
+                         const uint8_t* pad, int dtype, float* row_probs_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* MSATransformer.forward (model.py:338-416) for one MSA.
+ *   tokens [R,C] int64 -> x (caller-provided fp32 [R*C, D] buffer; holds the final
+ *   emb_layer_norm_after output on return), row_attn_out [N,H,C,C] fp32 or NULL,
+ *   rep_out: host array of num_layers+1 device pointers (or NULL entries): rep_out[l] receives a
+ *   copy of the hidden state after l layers for l < N (model.py:393-394); entry N is ignored
+ *   (x itself is representation N).  logits_out [R*C, vocab] fp32 or NULL (LM head skipped).
+ *   has_pad: 0 = the caller knows there is no <pad> token (padding_mask None, model.py:347-348). */
+int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int R, int C, int has_pad, int dtype,
+                       float* x, float* row_attn_out, float* const* rep_out, float* logits_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNAMSM_B200_H_ */

@@ -1,0 +1,119 @@
+"""ctypes binding of librnamsm_b200.so (C ABI: include/rnamsm_b200.h).
+
+The product path has NO fallback: if the shared library is missing or fails to load, importing
+this module raises, and every op raises ``RuntimeError`` carrying ``rnamsm_last_error()`` when a
+call returns non-zero.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "librnamsm_b200.so")
+
+F32, BF16 = 0, 1
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+
+_vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
+
+
+class AttnWeights(C.Structure):
+    _fields_ = [("ln_w", _vp), ("ln_b", _vp), ("w_qkv", _vp), ("b_qkv", _vp), ("w_out", _vp), ("b_out", _vp)]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [("row", AttnWeights), ("col", AttnWeights), ("ffn_ln_w", _vp), ("ffn_ln_b", _vp),
+                ("fc1_w", _vp), ("fc1_b", _vp), ("fc2_w", _vp), ("fc2_b", _vp)]
+
+
+class ModelWeights(C.Structure):
+    _fields_ = [("num_layers", _i), ("embed_dim", _i), ("num_heads", _i), ("ffn_dim", _i), ("vocab", _i),
+                ("n_pos", _i), ("pad_idx", _i), ("ln_eps", _f),
+                ("tok_emb", _vp), ("pos_emb", _vp), ("row_pos", _vp),
+                ("ln_before_w", _vp), ("ln_before_b", _vp), ("ln_after_w", _vp), ("ln_after_b", _vp),
+                ("lm_dense_w", _vp), ("lm_dense_b", _vp), ("lm_ln_w", _vp), ("lm_ln_b", _vp), ("lm_bias", _vp),
+                ("layers", C.POINTER(LayerWeights))]
+
+
+# name -> (restype, argtypes); every symbol include/rnamsm_b200.h declares
+SIGNATURES = {
+    "rnamsm_version": (_i, []),
+    "rnamsm_last_error": (C.c_char_p, []),
+    "rnamsm_device_check": (_i, []),
+    "rnamsm_launch_count": (_ll, []),
+    "rnamsm_embed_layernorm": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "rnamsm_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _f, _vp]),
+    "rnamsm_linear": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "rnamsm_row_attn_logits": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "rnamsm_row_attn_splits": (_i, [_i, _i, _i, _i]),
+    "rnamsm_row_softmax": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "rnamsm_row_attn_av": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "rnamsm_col_attn": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rnamsm_vocab_proj": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "rnamsm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "rnamsm_layer_forward": (_i, [C.POINTER(LayerWeights), _i, _i, _i, _f, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "rnamsm_msa_forward": (_i, [C.POINTER(ModelWeights), _vp, _i, _i, _i, _i, _vp, _vp, C.POINTER(_vp), _vp, _vp,
+                                _sz, _vp]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python rna-msm_b200/build.py` "
+        "(nvcc, sm_100a).  rnamsm_b200 has no CPU / PyTorch fallback.")
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = ABI mismatch, fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+assert lib.rnamsm_version() == 1, "librnamsm_b200.so ABI version mismatch"
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.rnamsm_last_error().decode(errors="replace")
+        raise RuntimeError(f"rnamsm_b200 {what} failed (status {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"rnamsm_b200: {what} must be a CUDA tensor (got {t.device}); this package is the B200 "
+            "CUDA path and has no CPU fallback")
+
+
+_checked_devices = set()
+
+
+def device_check(device: torch.device) -> None:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _checked_devices:
+        return
+    with torch.cuda.device(idx):
+        check(lib.rnamsm_device_check(), "device_check")
+    _checked_devices.add(idx)
+
+
+def dtype_code(precision: str) -> int:
+    if precision in ("bf16", "bfloat16"):
+        return BF16
+    if precision in ("fp32", "float32", "f32"):
+        return F32
+    raise ValueError(f"unknown precision {precision!r} (expected 'bf16' or 'fp32')")
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return torch.bfloat16 if code == BF16 else torch.float32

@@ -1,0 +1,324 @@
+// C ABI of librnamsm_b200.so (declared in include/rnamsm_b200.h) and the host-side drivers that
+// chain the kernels into one AxialTransformerLayer (modules.py:242-267) / one MSATransformer
+// forward (model.py:338-416).  No allocation, no synchronisation: everything is enqueued on the
+// caller's stream against caller-owned buffers.
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/rnamsm_b200.h"
+#include "common.cuh"
+#include "launch.h"
+
+namespace rnamsm {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+      return 1;
+    }
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA base pointer %p is not 16-byte aligned", base);
+    return 1;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) {
+        set_error("TMA stride %llu (dim %d) is not a multiple of 16 bytes", (unsigned long long)gstr[i - 1], i);
+        return 1;
+      }
+    }
+  }
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+    return 1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Workspace plan for one R x C MSA (bytes, every region 256 B aligned):
+//   xn      [T, D]      compute dtype   LayerNorm output feeding the next GEMM
+//   qkvh    [T, 4D|F]   compute dtype   q|k|v (3D) + attention context (D); aliased by the FFN hidden
+//   partial [S, H, C, C] fp32           split-K tied logits
+//   probs   [H, C, ldp] compute dtype   softmax probabilities for the AV GEMM (bf16 mode only)
+//   map     [H, C, C]   fp32            scratch attention map when the caller does not want it
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  size_t el;  // bytes per element of the compute dtype
+  int splits, ldp;
+  size_t off_xn, off_qkvh, off_partial, off_probs, off_map, total;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int pick_splits(int R, int C, int H, int dtype) {
+  if (dtype == RNAMSM_BF16) return row_logits_splits_bf16(R, C, H);
+  const long long tiles = (long long)H * ceil_div(C, 128) * ceil_div(C, 128);
+  int want = (int)std::max<long long>(1, (2 * 148) / std::max<long long>(1, tiles));
+  want = std::max(1, std::min(want, std::max(1, R / 4)));
+  const int rps = ceil_div(R, want);
+  return ceil_div(R, rps);
+}
+
+static Plan make_plan(int R, int C, int D, int H, int F, int dtype) {
+  Plan p{};
+  const size_t T = (size_t)R * C;
+  p.el = dtype == RNAMSM_BF16 ? 2 : 4;
+  p.splits = pick_splits(R, C, H, dtype);
+  p.ldp = dtype == RNAMSM_BF16 ? (C + 7) / 8 * 8 : C;
+  size_t o = 0;
+  p.off_xn = o;      o += align256(T * D * p.el);
+  p.off_qkvh = o;    o += align256(T * (size_t)std::max(4 * D, F) * p.el);
+  p.off_partial = o; o += align256((size_t)p.splits * H * C * C * 4);
+  p.off_probs = o;   o += align256(dtype == RNAMSM_BF16 ? (size_t)H * C * p.ldp * p.el : 0);
+  p.off_map = o;     o += align256((size_t)H * C * C * 4);
+  p.total = o;
+  return p;
+}
+
+static int linear_any(const void* x, const void* W, long long M, int N, int K, int dtype, const LinearEpilogue& e,
+                      void* out, cudaStream_t st) {
+  if (dtype == RNAMSM_BF16) return launch_linear_bf16(x, W, M, N, K, e, out, st);
+  if (dtype == RNAMSM_F32)
+    return launch_linear_f32((const float*)x, (const float*)W, M, N, K, e, (float*)out, st);
+  set_error("unknown dtype %d", dtype);
+  return 2;
+}
+
+static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, float eps, float* x, int R, int C,
+                         const uint8_t* pad, int dtype, float* row_probs_out, uint8_t* ws, const Plan& p,
+                         cudaStream_t st) {
+  const long long T = (long long)R * C;
+  void* xn = ws + p.off_xn;
+  uint8_t* qkv = ws + p.off_qkvh;
+  void* ctx = qkv + (size_t)T * 3 * D * p.el;
+  float* partial = reinterpret_cast<float*>(ws + p.off_partial);
+  void* probs_lp = dtype == RNAMSM_BF16 ? (void*)(ws + p.off_probs) : nullptr;
+  float* map = row_probs_out ? row_probs_out : reinterpret_cast<float*>(ws + p.off_map);
+  int rc;
+
+  // ---- tied row attention: x += out_proj(AV(softmax(sum_r q k^T)))   modules.py:385-401, 802-821
+  if ((rc = launch_layernorm(x, w->row.ln_w, w->row.ln_b, xn, dtype, T, D, eps, st))) return rc;
+  {
+    const float scaling = (1.0f / sqrtf(64.f)) / sqrtf((float)R);  // align_scaling, modules.py:713-715
+    LinearEpilogue e{RNAMSM_EPI_BIAS, w->row.b_qkv, scaling, D, pad};
+    if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, dtype, e, qkv, st))) return rc;
+  }
+  if (dtype == RNAMSM_BF16) {
+    if ((rc = launch_row_logits_bf16(qkv, R, C, H, partial, p.splits, st))) return rc;
+  } else {
+    if ((rc = launch_row_logits_f32((const float*)qkv, R, C, H, partial, p.splits, st))) return rc;
+  }
+  // key mask comes from MSA row 0 (padding_mask[:, 0], modules.py:780-784) = first C entries of pad
+  if ((rc = launch_row_softmax(partial, p.splits, H, C, pad, map, probs_lp, p.ldp, dtype, st))) return rc;
+  if (dtype == RNAMSM_BF16) {
+    if ((rc = launch_row_av_bf16(probs_lp, p.ldp, qkv, R, C, H, ctx, st))) return rc;
+  } else {
+    if ((rc = launch_row_av_f32(map, C, (const float*)qkv, R, C, H, (float*)ctx, st))) return rc;
+  }
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->row.b_out, 1.f, 0, nullptr};
+    if ((rc = linear_any(ctx, w->row.w_out, T, D, D, dtype, e, x, st))) return rc;
+  }
+
+  // ---- column attention over the MSA depth                           modules.py:875-945
+  if ((rc = launch_layernorm(x, w->col.ln_w, w->col.ln_b, xn, dtype, T, D, eps, st))) return rc;
+  if (R == 1) {
+    // single-row shortcut: out_proj(v_proj(x)), modules.py:882-894.  Project with the v rows only.
+    LinearEpilogue ev{RNAMSM_EPI_BIAS, w->col.b_qkv + 2 * D, 1.f, 0, nullptr};
+    const void* wv = (const uint8_t*)w->col.w_qkv + (size_t)2 * D * D * p.el;
+    if ((rc = linear_any(xn, wv, T, D, D, dtype, ev, ctx, st))) return rc;
+  } else {
+    LinearEpilogue e{RNAMSM_EPI_BIAS, w->col.b_qkv, 1.0f / sqrtf(64.f), D, nullptr};  // q *= scaling, :905
+    if ((rc = linear_any(xn, w->col.w_qkv, T, 3 * D, D, dtype, e, qkv, st))) return rc;
+    if (dtype == RNAMSM_BF16) {
+      if ((rc = launch_col_attn_bf16(qkv, R, C, H, pad, ctx, st))) return rc;
+    } else {
+      if ((rc = launch_col_attn_f32((const float*)qkv, R, C, H, pad, (float*)ctx, st))) return rc;
+    }
+  }
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->col.b_out, 1.f, 0, nullptr};
+    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, dtype, e, x, st))) return rc;
+  }
+
+  // ---- feed-forward: x += fc2(gelu(fc1(LN(x))))                        modules.py:423-427
+  if ((rc = launch_layernorm(x, w->ffn_ln_w, w->ffn_ln_b, xn, dtype, T, D, eps, st))) return rc;
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_GELU, w->fc1_b, 1.f, 0, nullptr};
+    if ((rc = linear_any(xn, w->fc1_w, T, F, D, dtype, e, qkv, st))) return rc;
+  }
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->fc2_b, 1.f, 0, nullptr};
+    if ((rc = linear_any(qkv, w->fc2_w, T, D, F, dtype, e, x, st))) return rc;
+  }
+  return 0;
+}
+
+}  // namespace rnamsm
+
+using namespace rnamsm;
+
+extern "C" {
+
+int rnamsm_version(void) { return RNAMSM_ABI_VERSION; }
+const char* rnamsm_last_error(void) { return get_error(); }
+long long rnamsm_launch_count(void) { return launch_count(); }
+
+int rnamsm_device_check(void) {
+  int dev = 0;
+  RNAMSM_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  RNAMSM_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  RNAMSM_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  RNAMSM_REQUIRE(major == 10, "rnamsm_b200 is built for sm_100a (B200); device %d is sm_%d%d", dev, major, minor);
+  return 0;
+}
+
+int rnamsm_embed_layernorm(const int64_t* tokens, int R, int C, const float* tok_emb, int vocab, const float* pos_emb,
+                           int n_pos, const float* row_pos, const float* ln_w, const float* ln_b, int D, int pad_idx,
+                           float eps, float* x_out, uint8_t* pad_out, void* stream) {
+  return launch_embed_ln(tokens, R, C, tok_emb, vocab, pos_emb, n_pos, row_pos, ln_w, ln_b, D, pad_idx, eps, x_out,
+                         pad_out, (cudaStream_t)stream);
+}
+
+int rnamsm_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
+                     float eps, void* stream) {
+  return launch_layernorm(x, w, b, y, y_dtype, n_rows, D, eps, (cudaStream_t)stream);
+}
+
+int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, int N, int K, int dtype, int epilogue,
+                  float q_scale, int q_cols, const uint8_t* row_mask, void* out, void* stream) {
+  RNAMSM_REQUIRE(epilogue >= 0 && epilogue <= 2, "rnamsm_linear: unknown epilogue %d", epilogue);
+  LinearEpilogue e{epilogue, bias, q_scale, q_cols, row_mask};
+  return linear_any(x, W, M, N, K, dtype, e, out, (cudaStream_t)stream);
+}
+
+int rnamsm_row_attn_splits(int R, int C, int H, int dtype) { return pick_splits(R, C, H, dtype); }
+
+int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, float* partial, int n_splits, void* stream) {
+  if (dtype == RNAMSM_BF16) return launch_row_logits_bf16(qkv, R, C, H, partial, n_splits, (cudaStream_t)stream);
+  return launch_row_logits_f32((const float*)qkv, R, C, H, partial, n_splits, (cudaStream_t)stream);
+}
+
+int rnamsm_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float* probs_out,
+                       void* probs_lp, int ld_lp, int dtype, void* stream) {
+  return launch_row_softmax(partial, n_splits, H, C, key_pad, probs_out, probs_lp, ld_lp, dtype, (cudaStream_t)stream);
+}
+
+int rnamsm_row_attn_av(const void* probs, int ldp, const void* qkv, int R, int C, int H, int dtype, void* ctx,
+                       void* stream) {
+  if (dtype == RNAMSM_BF16) return launch_row_av_bf16(probs, ldp, qkv, R, C, H, ctx, (cudaStream_t)stream);
+  return launch_row_av_f32((const float*)probs, ldp, (const float*)qkv, R, C, H, (float*)ctx, (cudaStream_t)stream);
+}
+
+int rnamsm_col_attn(const void* qkv, int R, int C, int H, int dtype, const uint8_t* pad, void* ctx, void* stream) {
+  RNAMSM_REQUIRE(R >= 2, "rnamsm_col_attn: R=%d (the R == 1 shortcut is out_proj(v_proj(x)))", R);
+  if (dtype == RNAMSM_BF16) return launch_col_attn_bf16(qkv, R, C, H, pad, ctx, (cudaStream_t)stream);
+  return launch_col_attn_f32((const float*)qkv, R, C, H, pad, (float*)ctx, (cudaStream_t)stream);
+}
+
+int rnamsm_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
+                      void* stream) {
+  return launch_vocab_proj(h, E, bias, M, V, D, out, (cudaStream_t)stream);
+}
+
+size_t rnamsm_workspace_bytes(int R, int C, int D, int H, int F, int dtype) {
+  if (R <= 0 || C <= 0) return 0;
+  return make_plan(R, C, D, H, F, dtype).total;
+}
+
+int rnamsm_layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, float ln_eps, float* x, int R, int C,
+                         const uint8_t* pad, int dtype, float* row_probs_out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  RNAMSM_REQUIRE(D == H * 64, "layer_forward: head_dim must be 64 (D=%d H=%d)", D, H);
+  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || dtype == RNAMSM_BF16, "layer_forward: unknown dtype %d", dtype);
+  const Plan p = make_plan(R, C, D, H, F, dtype);
+  RNAMSM_REQUIRE(workspace_bytes >= p.total, "layer_forward: workspace %zu < required %zu", workspace_bytes, p.total);
+  RNAMSM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "layer_forward: workspace must be 256 B aligned");
+  return layer_forward(w, D, H, F, ln_eps, x, R, C, pad, dtype, row_probs_out, (uint8_t*)workspace, p,
+                       (cudaStream_t)stream);
+}
+
+int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int R, int C, int has_pad, int dtype,
+                       float* x, float* row_attn_out, float* const* rep_out, float* logits_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->embed_dim, H = m->num_heads, F = m->ffn_dim, N = m->num_layers;
+  RNAMSM_REQUIRE(D == H * 64, "msa_forward: head_dim must be 64 (D=%d H=%d)", D, H);
+  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || dtype == RNAMSM_BF16, "msa_forward: unknown dtype %d", dtype);
+  RNAMSM_REQUIRE(R >= 1 && C >= 1, "msa_forward: empty MSA (R=%d C=%d)", R, C);
+  const Plan p = make_plan(R, C, D, H, F, dtype);
+  const size_t T = (size_t)R * C;
+  const size_t pad_bytes = (T + 255) & ~(size_t)255;
+  RNAMSM_REQUIRE(workspace_bytes >= p.total + pad_bytes, "msa_forward: workspace %zu < required %zu", workspace_bytes,
+                 p.total + pad_bytes);
+  RNAMSM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "msa_forward: workspace must be 256 B aligned");
+  uint8_t* ws = (uint8_t*)workspace;
+  uint8_t* pad = ws + p.total;
+  int rc;
+  if ((rc = launch_embed_ln(tokens, R, C, m->tok_emb, m->vocab, m->pos_emb, m->n_pos, m->row_pos, m->ln_before_w,
+                            m->ln_before_b, D, m->pad_idx, m->ln_eps, x, pad, st)))
+    return rc;
+  const uint8_t* pad_arg = has_pad ? pad : nullptr;
+  for (int l = 0; l < N; ++l) {
+    if (rep_out && rep_out[l]) RNAMSM_CHECK_CUDA(cudaMemcpyAsync(rep_out[l], x, T * D * 4, cudaMemcpyDeviceToDevice, st));
+    float* map = row_attn_out ? row_attn_out + (size_t)l * H * C * C : nullptr;
+    if ((rc = layer_forward(&m->layers[l], D, H, F, m->ln_eps, x, R, C, pad_arg, dtype, map, ws, p, st))) return rc;
+  }
+  // emb_layer_norm_after in place (model.py:396): fp32 -> fp32, each warp reads its row before writing it
+  if ((rc = launch_layernorm(x, m->ln_after_w, m->ln_after_b, x, RNAMSM_F32, (long long)T, D, m->ln_eps, st))) return rc;
+  if (logits_out) {
+    // RobertaLMHead (modules.py:313-319): dense -> erf-GELU -> LayerNorm -> tied projection + bias
+    // The head is 0.6 % of the forward's flops and feeds no inference output; it runs in fp32 on
+    // the FFMA kernels in both modes (fp32 weights), reusing the q|k|v|ctx scratch region.
+    uint8_t* hbuf = ws + p.off_qkvh;
+    float* h32 = reinterpret_cast<float*>(hbuf + align256(T * D * 4));
+    LinearEpilogue e{RNAMSM_EPI_BIAS_GELU, m->lm_dense_b, 1.f, 0, nullptr};
+    if ((rc = launch_linear_f32(x, m->lm_dense_w, (long long)T, D, D, e, (float*)hbuf, st))) return rc;
+    if ((rc = launch_layernorm((const float*)hbuf, m->lm_ln_w, m->lm_ln_b, h32, RNAMSM_F32, (long long)T, D, m->ln_eps, st)))
+      return rc;
+    if ((rc = launch_vocab_proj(h32, m->tok_emb, m->lm_bias, (long long)T, m->vocab, D, logits_out, st))) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+// HBM-bound kernels of the RNA-MSM forward: embedding gather + LayerNorm (K1), LayerNorm (K2/K9),
+// tied-attention softmax / map export (K5) and the 12-wide tied LM-head projection (K9b).
+// All are one-warp-per-row, 128-bit vectorised, fp32 statistics.
+#include "common.cuh"
+#include "launch.h"
+
+namespace rnamsm {
+
+constexpr int kMaxVec = 8;  // D <= 8 * 128 = 1024 features per token
+
+// -------------------------------------------------------------------------------------------
+// Warp-level LayerNorm of a row held as nv float4 per lane (features lane*4 + i*128 ..).
+// Two-pass (mean, then centred variance) in registers: matches nn.LayerNorm's biased variance.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_layernorm(float4 (&v)[kMaxVec], int nv, int D, float eps,
+                                               const float* __restrict__ w, const float* __restrict__ b,
+                                               int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (i < nv) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (i < nv) {
+      const int f = lane * 4 + i * 128;
+      const float4 ww = *reinterpret_cast<const float4*>(w + f);
+      const float4 bb = *reinterpret_cast<const float4*>(b + f);
+      v[i].x = v[i].x * rstd * ww.x + bb.x;
+      v[i].y = v[i].y * rstd * ww.y + bb.y;
+      v[i].z = v[i].z * rstd * ww.z + bb.z;
+      v[i].w = v[i].w * rstd * ww.w + bb.w;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K1: grid (ceil(C / kColsPerBlock), R); each block first scans its row's non-pad prefix up to
+// its column range (positions = cumsum(tok != pad) * (tok != pad) + pad_idx, modules.py:286-291)
+// then one warp per token gathers E_tok[tok] + E_pos[pos] + p_row[r], LayerNorms, zeroes pads.
+// -------------------------------------------------------------------------------------------
+constexpr int kEmbWarps = 8;
+constexpr int kColsPerBlock = 64;
+
+__global__ void __launch_bounds__(kEmbWarps * 32)
+embed_ln_kernel(const int64_t* __restrict__ tokens, int R, int C, const float* __restrict__ tok_emb, int vocab,
+                const float* __restrict__ pos_emb, int n_pos, const float* __restrict__ row_pos,
+                const float* __restrict__ ln_w, const float* __restrict__ ln_b, int D, int pad_idx, float eps,
+                float* __restrict__ x_out, uint8_t* __restrict__ pad_out) {
+  __shared__ int s_pos[kColsPerBlock];
+  __shared__ int s_tok[kColsPerBlock];
+  const int r = blockIdx.y;
+  const int c0 = blockIdx.x * kColsPerBlock;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t* trow = tokens + (size_t)r * C;
+  if (warp == 0) {
+    int running = 0;
+    const int c_end = min(C, c0 + kColsPerBlock);
+    for (int base = 0; base < c_end; base += 32) {
+      const int c = base + lane;
+      const int tok = (c < c_end) ? (int)trow[c] : pad_idx;
+      const bool keep = (c < c_end) && (tok != pad_idx);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      const int incl = running + __popc(m & (0xffffffffu >> (31 - lane)));
+      if (c >= c0 && c < c_end) {
+        s_pos[c - c0] = keep ? incl + pad_idx : pad_idx;
+        s_tok[c - c0] = tok;
+      }
+      running += __popc(m);
+    }
+  }
+  __syncthreads();
+  const int nv = D / 128;
+  const float prow = row_pos ? row_pos[r] : 0.f;
+  for (int cc = warp; cc < kColsPerBlock; cc += kEmbWarps) {
+    const int c = c0 + cc;
+    if (c >= C) break;
+    int tok = s_tok[cc];
+    int pos = s_pos[cc];
+    const bool is_pad = (tok == pad_idx);
+    tok = min(max(tok, 0), vocab - 1);
+    pos = min(pos, n_pos - 1);  // host validates; clamp keeps the gather in bounds regardless
+    float4 v[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const int f = lane * 4 + i * 128;
+        const float4 a = *reinterpret_cast<const float4*>(tok_emb + (size_t)tok * D + f);
+        const float4 p = *reinterpret_cast<const float4*>(pos_emb + (size_t)pos * D + f);
+        v[i] = make_float4(a.x + p.x + prow, a.y + p.y + prow, a.z + p.z + prow, a.w + p.w + prow);
+      }
+    warp_layernorm(v, nv, D, eps, ln_w, ln_b, lane);
+    float* dst = x_out + ((size_t)r * C + c) * D;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        if (is_pad) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // x * (1 - pad), model.py:366-367
+        *reinterpret_cast<float4*>(dst + lane * 4 + i * 128) = v[i];
+      }
+    if (pad_out && lane == 0) pad_out[(size_t)r * C + c] = is_pad ? 1 : 0;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// K2: LayerNorm rows of fp32 x -> fp32 or bf16 y.  One warp per row, kLnWarps rows per block.
+// -------------------------------------------------------------------------------------------
+constexpr int kLnWarps = 8;
+
+template <bool kOutBf16>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_kernel(const float* x, const float* __restrict__ w, const float* __restrict__ b,
+                 void* y, long long n_rows, int D, float eps) {  // x may alias y (in-place final LN)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = D / 128;
+  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < n_rows;
+       row += (long long)gridDim.x * kLnWarps) {
+    const float* src = x + (size_t)row * D;
+    float4 v[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) v[i] = *reinterpret_cast<const float4*>(src + lane * 4 + i * 128);
+    warp_layernorm(v, nv, D, eps, w, b, lane);
+    if constexpr (kOutBf16) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + (size_t)row * D;
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i)
+        if (i < nv) {
+          uint2 pk = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+          *reinterpret_cast<uint2*>(dst + lane * 4 + i * 128) = pk;
+        }
+    } else {
+      float* dst = reinterpret_cast<float*>(y) + (size_t)row * D;
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i)
+        if (i < nv) *reinterpret_cast<float4*>(dst + lane * 4 + i * 128) = v[i];
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// K5: one warp per (head, query column i).  Sums the split-K partial logits, applies the key
+// mask, softmax over j, writes the fp32 map (the exported attention map) and the low-precision
+// copy that feeds the AV GEMM.  Three passes over the (L2-resident) partial rows keep register
+// use independent of C.
+// -------------------------------------------------------------------------------------------
+constexpr int kSmWarps = 4;
+
+template <bool kLpBf16>
+__global__ void __launch_bounds__(kSmWarps * 32)
+row_softmax_kernel(const float* __restrict__ partial, int n_splits, int H, int C,
+                   const uint8_t* __restrict__ key_pad, float* __restrict__ probs_out, void* __restrict__ probs_lp,
+                   int ld_lp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kSmWarps + warp;  // h * C + i
+  if (row >= (long long)H * C) return;
+  const size_t split_stride = (size_t)H * C * C;
+  const float* src = partial + (size_t)row * C;
+  auto logit = [&](int j) -> float {
+    float a = 0.f;
+    for (int s = 0; s < n_splits; ++s) a += src[s * split_stride + j];
+    if (key_pad && key_pad[j]) a = -10000.f;  // masked_fill, modules.py:780-784
+    return a;
+  };
+  float mx = -INFINITY;
+  for (int j = lane; j < C; j += 32) mx = fmaxf(mx, logit(j));
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < C; j += 32) sum += __expf(logit(j) - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  float* dst = probs_out + (size_t)row * C;
+  for (int j = lane; j < ld_lp || j < C; j += 32) {
+    const float p = (j < C) ? __expf(logit(j) - mx) * inv : 0.f;
+    if (j < C) dst[j] = p;
+    if (probs_lp && j < ld_lp) {
+      if constexpr (kLpBf16)
+        reinterpret_cast<__nv_bfloat16*>(probs_lp)[(size_t)row * ld_lp + j] = __float2bfloat16(p);
+      else
+        reinterpret_cast<float*>(probs_lp)[(size_t)row * ld_lp + j] = p;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// K9b: logits[m, v] = h[m, :] . E[v, :] + bias[v]; one warp per token, V <= 32 outputs.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vocab_proj_kernel(const float* __restrict__ h, const float* __restrict__ E, const float* __restrict__ bias,
+                  long long M, int V, int D, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = D / 128;
+  for (long long m = (long long)blockIdx.x * 8 + warp; m < M; m += (long long)gridDim.x * 8) {
+    float4 v[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) v[i] = *reinterpret_cast<const float4*>(h + (size_t)m * D + lane * 4 + i * 128);
+    float mine = 0.f;
+    for (int o = 0; o < V; ++o) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i)
+        if (i < nv) {
+          const float4 e = *reinterpret_cast<const float4*>(E + (size_t)o * D + lane * 4 + i * 128);
+          acc += v[i].x * e.x + v[i].y * e.y + v[i].z * e.z + v[i].w * e.w;
+        }
+      acc = warp_sum(acc);
+      if (lane == o) mine = acc + bias[o];
+    }
+    if (lane < V) out[(size_t)m * V + lane] = mine;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Launchers
+// -------------------------------------------------------------------------------------------
+int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, int vocab, const float* pos_emb,
+                    int n_pos, const float* row_pos, const float* ln_w, const float* ln_b, int D, int pad_idx,
+                    float eps, float* x_out, uint8_t* pad_out, cudaStream_t st) {
+  RNAMSM_REQUIRE(D % 128 == 0 && D <= 128 * kMaxVec, "embed_layernorm: D=%d must be a multiple of 128 <= 1024", D);
+  RNAMSM_REQUIRE(R > 0 && C > 0 && R <= 65535, "embed_layernorm: bad shape R=%d C=%d", R, C);
+  dim3 grid(ceil_div(C, kColsPerBlock), R);
+  embed_ln_kernel<<<grid, kEmbWarps * 32, 0, st>>>(tokens, R, C, tok_emb, vocab, pos_emb, n_pos, row_pos, ln_w,
+                                                  ln_b, D, pad_idx, eps, x_out, pad_out);
+  count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
+                     float eps, cudaStream_t st) {
+  RNAMSM_REQUIRE(D % 128 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d must be a multiple of 128 <= 1024", D);
+  if (n_rows <= 0) return 0;
+  const int blocks = (int)std::min<long long>((n_rows + kLnWarps - 1) / kLnWarps, 148LL * 32);
+  if (y_dtype == 1)
+    layernorm_kernel<true><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
+  else
+    layernorm_kernel<false><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
+  count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float* probs_out,
+                       void* probs_lp, int ld_lp, int dtype, cudaStream_t st) {
+  RNAMSM_REQUIRE(n_splits >= 1 && H > 0 && C > 0, "row_softmax: bad shape");
+  const long long rows = (long long)H * C;
+  const int blocks = (int)((rows + kSmWarps - 1) / kSmWarps);
+  if (probs_lp == nullptr) ld_lp = 0;
+  if (dtype == 1)
+    row_softmax_kernel<true><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, probs_out, probs_lp, ld_lp);
+  else
+    row_softmax_kernel<false><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, probs_out, probs_lp, ld_lp);
+  count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
+                      cudaStream_t st) {
+  RNAMSM_REQUIRE(V <= 32 && D % 128 == 0 && D <= 128 * kMaxVec, "vocab_proj: V=%d D=%d unsupported", V, D);
+  if (M <= 0) return 0;
+  const int blocks = (int)std::min<long long>((M + 7) / 8, 148LL * 16);
+  vocab_proj_kernel<<<blocks, 256, 0, st>>>(h, E, bias, M, V, D, out);
+  count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rnamsm

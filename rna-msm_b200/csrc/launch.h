@@ -1,0 +1,50 @@
+// Internal launcher declarations shared by the translation units of librnamsm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+namespace rnamsm {
+
+void count_launch(int n = 1);
+long long launch_count();
+
+// elementwise.cu
+int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, int vocab, const float* pos_emb,
+                    int n_pos, const float* row_pos, const float* ln_w, const float* ln_b, int D, int pad_idx,
+                    float eps, float* x_out, uint8_t* pad_out, cudaStream_t st);
+int launch_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
+                     float eps, cudaStream_t st);
+int launch_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float* probs_out,
+                       void* probs_lp, int ld_lp, int dtype, cudaStream_t st);
+int launch_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
+                      cudaStream_t st);
+
+// Epilogue description shared by the fp32 (FFMA) and bf16 (tcgen05) linear kernels.
+struct LinearEpilogue {
+  int kind;                 // RNAMSM_EPI_*
+  const float* bias;        // [N]
+  float q_scale;            // applied to columns [0, q_cols) after the bias
+  int q_cols;
+  const uint8_t* row_mask;  // [M] or nullptr; zeroes columns [0, q_cols) of masked rows
+};
+
+// simt_f32.cu -- fp32 parity path
+int launch_linear_f32(const float* x, const float* W, long long M, int N, int K, const LinearEpilogue& epi, float* out,
+                      cudaStream_t st);
+int launch_row_logits_f32(const float* qkv, int R, int C, int H, float* partial, int n_splits, cudaStream_t st);
+int launch_row_av_f32(const float* probs, int ldp, const float* qkv, int R, int C, int H, float* ctx, cudaStream_t st);
+int launch_col_attn_f32(const float* qkv, int R, int C, int H, const uint8_t* pad, float* ctx, cudaStream_t st);
+
+// umma_gemm.cu -- bf16 tcgen05 path
+int launch_linear_bf16(const void* x, const void* W, long long M, int N, int K, const LinearEpilogue& epi, void* out,
+                       cudaStream_t st);
+int launch_row_logits_bf16(const void* qkv, int R, int C, int H, float* partial, int n_splits, cudaStream_t st);
+int launch_row_av_bf16(const void* probs, int ldp, const void* qkv, int R, int C, int H, void* ctx, cudaStream_t st);
+int row_logits_splits_bf16(int R, int C, int H);
+
+// col_attn_umma.cu
+int launch_col_attn_bf16(const void* qkv, int R, int C, int H, const uint8_t* pad, void* ctx, cudaStream_t st);
+
+}  // namespace rnamsm

@@ -1,0 +1,100 @@
+"""Feature extraction, the B200 counterpart of ``RNA_MSM_Inference.py`` (reference lines 90-168):
+for every RNA id, MSA -> tokens -> ``MSATransformer`` -> ``<id>_atp.npy`` ``(120, L, L)`` f32 and
+``<id>_emb.npy`` ``(L, 768)`` f32, byte-compatible with what the ``_downstream_tasks`` SS / RSA
+predictors read.  Same knob names as the reference's hydra config (``data.*`` / ``model.*``),
+exposed through argparse because hydra is not a dependency here::
+
+    python -m rnamsm_b200.inference --root_path . --MSA_path results --MSA_list rna_id.txt \
+        --model_path pretrained/RNA_MSM_pretrained.ckpt
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .alphabet import Alphabet, Vocab, tokenize_msa
+from .model import MSATransformer
+
+
+def extract_features(results: Dict[str, object], vocab: Vocab, num_layers: int) -> Tuple[np.ndarray, np.ndarray]:
+    """RNA_MSM_Inference.py:150-166: strip BOS row/column, flatten (layer, head) -> 120 maps, and
+    take MSA row 0 of the final representation.  One D2H copy per output."""
+    attentions = results["row_attentions"]
+    start_idx = int(vocab.prepend_bos)
+    end_idx = attentions.size(-1) - int(vocab.append_eos)
+    attentions = attentions[..., start_idx:end_idx, start_idx:end_idx]
+    seqlen = attentions.size(-1)
+    atp = attentions.reshape(-1, seqlen, seqlen).cpu().numpy()
+    embedding = results["representations"][num_layers]
+    end_idx = embedding.size(-2) - int(vocab.append_eos)
+    emb = embedding[:, 0, start_idx:end_idx, :].squeeze(0).cpu().numpy()
+    return emb, atp
+
+
+def build_model(model_path: Optional[str], device: str = "cuda", precision: str = "bf16", embed_dim: int = 768,
+                num_attention_heads: int = 12, num_layers: int = 10, embed_positions_msa: bool = True,
+                max_tokens: int = 16384, max_seqlen: int = 1024, seed: int = 42) -> Tuple[MSATransformer, Vocab]:
+    alphabet = Alphabet.from_architecture("rna language")
+    vocab = Vocab.from_esm_alphabet(alphabet)
+    torch.manual_seed(seed)                                   # seed_everything(42), RNA_MSM_Inference.py:17
+    model = MSATransformer(vocab, embed_dim=embed_dim, num_attention_heads=num_attention_heads,
+                           num_layers=num_layers, embed_positions_msa=embed_positions_msa,
+                           max_tokens_per_msa=max_tokens, max_seqlen=max_seqlen, precision=precision)
+    if model_path:
+        ckpt = torch.load(model_path, map_location="cpu")
+        model.load_state_dict(ckpt["state_dict"] if "state_dict" in ckpt else ckpt, strict=True)
+    model = model.eval().to(device)
+    return model, vocab
+
+
+@torch.no_grad()
+def run_inference(model: MSATransformer, vocab: Vocab, root_path: str, MSA_path: str, rna_ids, max_seqs_per_msa=512,
+                  max_seqlen=1024, verbose=True) -> str:
+    save_feat_path = os.path.join(root_path, MSA_path)
+    os.makedirs(save_feat_path, exist_ok=True)
+    for rna_id in sorted(rna_ids):
+        msa_file = os.path.join(root_path, MSA_path, rna_id + ".a2m_msa2")
+        tokens = tokenize_msa(msa_file, vocab, max_seqs_per_msa, max_seqlen).unsqueeze(0)
+        results = model(tokens.to(model.device), repr_layers=[model.num_layers], need_head_weights=True,
+                        want_logits=False)
+        emb, atp = extract_features(results, vocab, model.num_layers)
+        np.save(os.path.join(save_feat_path, rna_id + "_atp.npy"), atp)
+        np.save(os.path.join(save_feat_path, rna_id + "_emb.npy"), emb)
+        if verbose:
+            print(f"{rna_id}: tokens {tuple(tokens.shape)} -> atp {atp.shape}, emb {emb.shape}")
+    if verbose:
+        print(f"Done! Generated files are saved at {save_feat_path}")
+    return save_feat_path
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--root_path", default=".")
+    ap.add_argument("--MSA_path", default="results")
+    ap.add_argument("--MSA_list", default="rna_id.txt")
+    ap.add_argument("--model_path", default=None, help="Lightning checkpoint ('state_dict'); random init if omitted")
+    ap.add_argument("--max_seqlen", type=int, default=1024)
+    ap.add_argument("--max_tokens", type=int, default=16384)
+    ap.add_argument("--max_seqs_per_msa", type=int, default=512)
+    ap.add_argument("--embed_dim", type=int, default=768)
+    ap.add_argument("--num_attention_heads", type=int, default=12)
+    ap.add_argument("--num_layers", type=int, default=10)
+    ap.add_argument("--no_embed_positions_msa", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    a = ap.parse_args(argv)
+    model, vocab = build_model(a.model_path, a.device, a.precision, a.embed_dim, a.num_attention_heads, a.num_layers,
+                               not a.no_embed_positions_msa, a.max_tokens, a.max_seqlen)
+    print(f"Maximum Number of MSA Seqs:{a.max_seqs_per_msa}")
+    print(f"Inference on: {model.device}")
+    with open(os.path.join(a.root_path, a.MSA_list)) as f:
+        ids = f.read().splitlines()
+    run_inference(model, vocab, a.root_path, a.MSA_path, ids, a.max_seqs_per_msa, a.max_seqlen)
+
+
+if __name__ == "__main__":
+    main()
