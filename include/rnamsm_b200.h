@@ -52,6 +52,15 @@ int rnamsm_device_check(void);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 long long rnamsm_launch_count(void);
 
+/* Optional device timing of every kernel launch by class (cudaEvents recorded on the launching
+ * stream around each launch).  enable(1) resets and starts recording, enable(0) stops;
+ * collect() synchronises the recorded events and returns the accumulated milliseconds and launch
+ * counts per class (arrays of rnamsm_profile_num_classes() entries).  Host-side, not thread-safe. */
+int rnamsm_profile_enable(int on);
+int rnamsm_profile_num_classes(void);
+const char* rnamsm_profile_class_name(int cls);
+int rnamsm_profile_collect(double* ms_out, long long* launches_out, int n);
+
 /* K1 -- token + learned-position + per-row scalar embedding, LayerNorm, pad zeroing.
  * Replaces model.py:346-367 and LearnedPositionalEmbedding.forward (modules.py:286-300).
  * tokens [R,C] int64; tok_emb [vocab,D]; pos_emb [n_pos,D]; row_pos [>=R] scalars or NULL;

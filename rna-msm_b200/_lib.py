@@ -44,6 +44,10 @@ SIGNATURES = {
     "rnamsm_last_error": (C.c_char_p, []),
     "rnamsm_device_check": (_i, []),
     "rnamsm_launch_count": (_ll, []),
+    "rnamsm_profile_enable": (_i, [_i]),
+    "rnamsm_profile_num_classes": (_i, []),
+    "rnamsm_profile_class_name": (C.c_char_p, [_i]),
+    "rnamsm_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_ll), _i]),
     "rnamsm_embed_layernorm": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "rnamsm_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _f, _vp]),
     "rnamsm_linear": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
@@ -117,3 +121,16 @@ def dtype_code(precision: str) -> int:
 
 def torch_dtype(code: int) -> torch.dtype:
     return torch.bfloat16 if code == BF16 else torch.float32
+
+
+def profile_enable(on: bool) -> None:
+    check(lib.rnamsm_profile_enable(int(on)), "profile_enable")
+
+
+def profile_collect():
+    """-> {class_name: (milliseconds, launches)} accumulated since profile_enable(True)."""
+    n = lib.rnamsm_profile_num_classes()
+    ms = (C.c_double * n)()
+    cnt = (_ll * n)()
+    check(lib.rnamsm_profile_collect(ms, cnt, n), "profile_collect")
+    return {lib.rnamsm_profile_class_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}

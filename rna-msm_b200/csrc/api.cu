@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "../../include/rnamsm_b200.h"
 #include "common.cuh"
@@ -27,6 +28,32 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- optional kernel-class timing ---------------------------------------------------------------
+struct ProfEvent { int cls; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof_events;
+static std::vector<cudaEvent_t> g_prof_pool;
+static const char* kClassNames[KC_COUNT] = {"embed_ln", "layernorm", "row_softmax", "vocab_proj", "linear_qkv",
+                                            "linear_fc1_gelu", "linear_out_resid", "linear_fc2_resid",
+                                            "row_logits", "row_av", "col_attn"};
+static cudaEvent_t prof_get_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+ProfScope::ProfScope(int c, cudaStream_t s) : cls(c), st(s), slot(nullptr) {
+  if (!g_prof_on) return;
+  ProfEvent ev{c, prof_get_event(), prof_get_event()};
+  cudaEventRecord(ev.a, st);
+  g_prof_events.push_back(ev);
+  slot = reinterpret_cast<void*>(g_prof_events.size());
+}
+ProfScope::~ProfScope() {
+  if (!slot) return;
+  cudaEventRecord(g_prof_events[reinterpret_cast<size_t>(slot) - 1].b, st);
+}
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
@@ -202,6 +229,30 @@ extern "C" {
 int rnamsm_version(void) { return RNAMSM_ABI_VERSION; }
 const char* rnamsm_last_error(void) { return get_error(); }
 long long rnamsm_launch_count(void) { return launch_count(); }
+
+int rnamsm_profile_enable(int on) {
+  for (auto& ev : g_prof_events) { g_prof_pool.push_back(ev.a); g_prof_pool.push_back(ev.b); }
+  g_prof_events.clear();
+  g_prof_on = on != 0;
+  return 0;
+}
+int rnamsm_profile_num_classes(void) { return KC_COUNT; }
+const char* rnamsm_profile_class_name(int i) { return (i >= 0 && i < KC_COUNT) ? kClassNames[i] : ""; }
+int rnamsm_profile_collect(double* ms_out, long long* launches_out, int n) {
+  RNAMSM_REQUIRE(n >= KC_COUNT, "profile_collect: need %d slots", (int)KC_COUNT);
+  for (int i = 0; i < n; ++i) { ms_out[i] = 0.0; launches_out[i] = 0; }
+  for (auto& ev : g_prof_events) {
+    RNAMSM_CHECK_CUDA(cudaEventSynchronize(ev.b));
+    float ms = 0.f;
+    RNAMSM_CHECK_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    ms_out[ev.cls] += ms;
+    launches_out[ev.cls] += 1;
+    g_prof_pool.push_back(ev.a);
+    g_prof_pool.push_back(ev.b);
+  }
+  g_prof_events.clear();
+  return 0;
+}
 
 int rnamsm_device_check(void) {
   int dev = 0;

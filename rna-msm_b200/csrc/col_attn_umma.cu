@@ -233,6 +233,7 @@ int launch_col_attn_bf16(const void* qkv, int R, int C, int H, const uint8_t* pa
   RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   dim3 grid(C, H, ceil_div(R, BQ));
   RNAMSM_REQUIRE(grid.z <= 65535, "col_attn_bf16: R too large");
+  ProfScope prof(KC_COL_ATTN, st);
   col_attn_umma_kernel<<<grid, 128, kSmem, st>>>(tq, tkv, R, C, H, pad, reinterpret_cast<__nv_bfloat16*>(ctx));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());

@@ -226,6 +226,7 @@ int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, i
   RNAMSM_REQUIRE(D % 128 == 0 && D <= 128 * kMaxVec, "embed_layernorm: D=%d must be a multiple of 128 <= 1024", D);
   RNAMSM_REQUIRE(R > 0 && C > 0 && R <= 65535, "embed_layernorm: bad shape R=%d C=%d", R, C);
   dim3 grid(ceil_div(C, kColsPerBlock), R);
+  ProfScope prof(KC_EMBED_LN, st);
   embed_ln_kernel<<<grid, kEmbWarps * 32, 0, st>>>(tokens, R, C, tok_emb, vocab, pos_emb, n_pos, row_pos, ln_w,
                                                   ln_b, D, pad_idx, eps, x_out, pad_out);
   count_launch();
@@ -238,6 +239,7 @@ int launch_layernorm(const float* x, const float* w, const float* b, void* y, in
   RNAMSM_REQUIRE(D % 128 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d must be a multiple of 128 <= 1024", D);
   if (n_rows <= 0) return 0;
   const int blocks = (int)std::min<long long>((n_rows + kLnWarps - 1) / kLnWarps, 148LL * 32);
+  ProfScope prof(KC_LAYERNORM, st);
   if (y_dtype == 1)
     layernorm_kernel<true><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
   else
@@ -253,6 +255,7 @@ int launch_row_softmax(const float* partial, int n_splits, int H, int C, const u
   const long long rows = (long long)H * C;
   const int blocks = (int)((rows + kSmWarps - 1) / kSmWarps);
   if (probs_lp == nullptr) ld_lp = 0;
+  ProfScope prof(KC_ROW_SOFTMAX, st);
   if (dtype == 1)
     row_softmax_kernel<true><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, probs_out, probs_lp, ld_lp);
   else
@@ -267,6 +270,7 @@ int launch_vocab_proj(const float* h, const float* E, const float* bias, long lo
   RNAMSM_REQUIRE(V <= 32 && D % 128 == 0 && D <= 128 * kMaxVec, "vocab_proj: V=%d D=%d unsupported", V, D);
   if (M <= 0) return 0;
   const int blocks = (int)std::min<long long>((M + 7) / 8, 148LL * 16);
+  ProfScope prof(KC_VOCAB_PROJ, st);
   vocab_proj_kernel<<<blocks, 256, 0, st>>>(h, E, bias, M, V, D, out);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());

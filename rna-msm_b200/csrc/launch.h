@@ -10,6 +10,20 @@ namespace rnamsm {
 void count_launch(int n = 1);
 long long launch_count();
 
+// Optional per-kernel-class device timing (cudaEvents on the launching stream), used by bench.py
+// for the live roofline figure and the per-kernel time shares.  Off by default: zero overhead.
+enum KernelClass {
+  KC_EMBED_LN = 0, KC_LAYERNORM, KC_ROW_SOFTMAX, KC_VOCAB_PROJ, KC_LINEAR_QKV, KC_LINEAR_FC1, KC_LINEAR_OUT,
+  KC_LINEAR_FC2, KC_ROW_LOGITS, KC_ROW_AV, KC_COL_ATTN, KC_COUNT
+};
+struct ProfScope {
+  int cls;
+  cudaStream_t st;
+  void* slot;
+  ProfScope(int cls, cudaStream_t st);
+  ~ProfScope();
+};
+
 // elementwise.cu
 int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, int vocab, const float* pos_emb,
                     int n_pos, const float* row_pos, const float* ln_w, const float* ln_b, int D, int pad_idx,
@@ -29,6 +43,13 @@ struct LinearEpilogue {
   int q_cols;
   const uint8_t* row_mask;  // [M] or nullptr; zeroes columns [0, q_cols) of masked rows
 };
+
+// Kernel class of a dense linear launch (for the timing breakdown): by epilogue and shape.
+inline int linear_class(int epi_kind, int N, int K) {
+  if (epi_kind == 1) return KC_LINEAR_FC1;
+  if (epi_kind == 2) return K > N ? KC_LINEAR_FC2 : KC_LINEAR_OUT;
+  return KC_LINEAR_QKV;
+}
 
 // simt_f32.cu -- fp32 parity path
 int launch_linear_f32(const float* x, const float* W, long long M, int N, int K, const LinearEpilogue& epi, float* out,

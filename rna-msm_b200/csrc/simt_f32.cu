@@ -109,6 +109,7 @@ int launch_linear_f32(const float* x, const float* W, long long M, int N, int K,
   LinearProb p{(int)M, N, K, x, W, out, epi};
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), 1);
   RNAMSM_REQUIRE(grid.y <= 65535, "linear_f32: M=%lld too large for this path", M);
+  ProfScope prof(linear_class(epi.kind, N, K), st);
   sgemm_kernel<<<grid, NT, 0, st>>>(p);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
@@ -146,6 +147,7 @@ int launch_row_logits_f32(const float* qkv, int R, int C, int H, float* partial,
   RNAMSM_REQUIRE(n_splits >= 1 && n_splits <= R, "row_logits_f32: n_splits=%d out of range for R=%d", n_splits, R);
   TiedLogitsProb p{C, C, R, C, H, 3 * H * 64, n_splits, ceil_div(R, n_splits), qkv, partial};
   dim3 grid(ceil_div(C, BN), ceil_div(C, BM), H * n_splits);
+  ProfScope prof(KC_ROW_LOGITS, st);
   sgemm_kernel<<<grid, NT, 0, st>>>(p);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
@@ -175,6 +177,7 @@ int launch_row_av_f32(const float* probs, int ldp, const float* qkv, int R, int 
   TiedAvProb p{C, R * 64, R, C, H, 3 * H * 64, ldp, probs, qkv, ctx};
   dim3 grid(ceil_div(R * 64, BN), ceil_div(C, BM), H);
   RNAMSM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "row_av_f32: grid too large");
+  ProfScope prof(KC_ROW_AV, st);
   sgemm_kernel<<<grid, NT, 0, st>>>(p);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
@@ -294,6 +297,7 @@ int launch_col_attn_f32(const float* qkv, int R, int C, int H, const uint8_t* pa
   RNAMSM_REQUIRE(R >= 1 && C >= 1 && H >= 1 && H <= 65535, "col_attn_f32: bad shape");
   dim3 grid(C, H, ceil_div(R, CQ));
   RNAMSM_REQUIRE(grid.z <= 65535, "col_attn_f32: R too large");
+  ProfScope prof(KC_COL_ATTN, st);
   constexpr int smem_bytes = 4 * HD * (CQ + 4) * (int)sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {

@@ -302,16 +302,13 @@ int num_sms() {
 }
 
 template <int kVariant>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBytes));
-    attr_set = true;
-  }
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int prof_class, cudaStream_t st) {
+  RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBytes));
   const long long total = (long long)g.m_tiles * g.n_tiles * g.batches * g.splits;
   RNAMSM_REQUIRE(total > 0 && total < (1LL << 31), "umma_gemm: tile count %lld out of range", total);
   const int grid = (int)std::min<long long>(total, num_sms());
+  ProfScope prof(prof_class, st);
   umma_gemm_kernel<kVariant><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, g);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
@@ -348,7 +345,7 @@ int launch_linear_bf16(const void* x, const void* W, long long M, int N, int K, 
   g.M = (int)M; g.N = N;
   g.epi_kind = epi.kind; g.bias = epi.bias; g.q_scale = epi.q_scale; g.q_cols = epi.q_cols; g.row_mask = epi.row_mask;
   g.out = out; g.ld_out = N;
-  return launch_variant<V_DENSE>(ta, tb, g, st);
+  return launch_variant<V_DENSE>(ta, tb, g, linear_class(epi.kind, N, K), st);
 }
 
 int row_logits_splits_bf16(int R, int C, int H) {
@@ -379,7 +376,7 @@ int launch_row_logits_bf16(const void* qkv, int R, int C, int H, float* partial,
   g.rows_per_split = rps;
   g.R = R; g.C = C; g.H = H; g.M = C; g.N = C;
   g.out = partial;
-  return launch_variant<V_TIED>(ta, tb, g, st);
+  return launch_variant<V_TIED>(ta, tb, g, KC_ROW_LOGITS, st);
 }
 
 int launch_row_av_bf16(const void* probs, int ldp, const void* qkv, int R, int C, int H, void* ctx, cudaStream_t st) {
@@ -405,7 +402,7 @@ int launch_row_av_bf16(const void* probs, int ldp, const void* qkv, int R, int C
   g.k_blocks = ceil_div(C, BLOCK_K);
   g.R = R; g.C = C; g.H = H; g.M = C; g.N = R;
   g.out = ctx; g.ld_out = H * 64;
-  return launch_variant<V_AV>(ta, tb, g, st);
+  return launch_variant<V_AV>(ta, tb, g, KC_ROW_AV, st);
 }
 
 }  // namespace rnamsm

@@ -1,0 +1,188 @@
+"""GPU parity of the whole hot path against the committed golden vectors (outputs of the
+reference's own fp32 forward, oracle/gen_golden.py) and against the CPU oracle on seeded inputs.
+
+Gates (BASELINE.json north_star): fp32 path max|d|/max|ref| <= 1e-4 on emb and atp;
+bf16 path <= 2e-2 plus identical row-argmax on >= 99 % of map rows.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import msa_ref as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import rnamsm_b200
+    return rnamsm_b200
+
+
+def build(pkg, g_or_seed, layers=10, sharpen=1.0, precision="fp32", embed_positions_msa=True):
+    vocab = pkg.Vocab(pkg.Alphabet())
+    model = pkg.MSATransformer(vocab, num_layers=layers, embed_positions_msa=embed_positions_msa, precision=precision)
+    sd = O.make_weights(int(g_or_seed), num_layers=layers, sharpen=float(sharpen),
+                        embed_positions_msa=embed_positions_msa)
+    model.load_state_dict(sd, strict=True)
+    return model.eval().cuda(), sd
+
+
+def argmax_agreement(a, b):
+    a = torch.as_tensor(a).reshape(-1, a.shape[-1])
+    b = torch.as_tensor(b).reshape(-1, b.shape[-1])
+    return float((a.argmax(-1) == b.argmax(-1)).float().mean())
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_pad", "ragged_sharp", "single_row", "batch2_pad", "mid_sharp"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_model_vs_reference_golden(pkg, golden_dir, name, precision):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    layers = int(g["layers"])
+    model, _ = build(pkg, g["wseed"], layers, g["sharpen"], precision)
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    out = model(tokens, repr_layers=[0, 1, layers], need_head_weights=True)
+    rows = torch.from_numpy(g["rep_rows"]).cuda()
+    tol = FP32_TOL if precision == "fp32" else BF16_TOL
+    errs = {
+        "rep0": O.rel_err(out["representations"][0][:, rows].cpu(), g["rep0"]),
+        "rep1": O.rel_err(out["representations"][1][:, rows].cpu(), g["rep1"]),
+        "rep_last": O.rel_err(out["representations"][layers][:, rows].cpu(), g["rep_last"]),
+        "logits": O.rel_err(out["logits"][:, rows].cpu(), g["logits"]),
+    }
+    ra = out["row_attentions"].cpu()
+    if "row_attentions" in g:
+        ref_ra = torch.from_numpy(g["row_attentions"])
+        errs["row_attn"] = O.rel_err(ra, ref_ra)
+        agree = argmax_agreement(ra, ref_ra)
+    else:
+        flat = ra.reshape(ra.shape[0], -1, ra.shape[-2], ra.shape[-1])
+        sel = flat[:, g["row_attentions_sel_idx"]]
+        errs["row_attn"] = O.rel_err(sel, g["row_attentions_sel"])
+        errs["row_attn_mean"] = O.rel_err(flat.mean(1), g["row_attentions_mean"])
+        agree = argmax_agreement(sel, torch.from_numpy(g["row_attentions_sel"]))
+    print(f"[{name}/{precision}] {errs} argmax_agree={agree:.4f}")
+    assert errs["rep0"] < 1e-5                       # K1 is fp32 in both modes
+    assert max(errs.values()) < tol, errs
+    if precision == "bf16" and float(g["sharpen"]) > 1:
+        assert agree >= 0.99
+    if "atp" in g:
+        emb, atp = pkg.extract_features(out, model.vocab, layers)
+        assert emb.dtype == np.float32 and atp.dtype == np.float32
+        assert emb.shape == g["emb"].shape and atp.shape == g["atp"].shape
+        assert O.rel_err(emb, g["emb"]) < tol and O.rel_err(atp, g["atp"]) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config1_2drb(pkg, golden_dir, precision):
+    """BASELINE config 1: the shipped 2DRB_1 MSA (first 512 rows), emb (35,768) + atp (120,35,35)."""
+    g = np.load(os.path.join(golden_dir, "2DRB_1.npz"))
+    model, _ = build(pkg, g["wseed"], 10, g["sharpen"], precision)
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    out = model(tokens, repr_layers=[10], need_head_weights=True, want_logits=False)
+    emb, atp = pkg.extract_features(out, model.vocab, 10)
+    assert emb.shape == (35, 768) and atp.shape == (120, 35, 35)
+    e_emb, e_atp = O.rel_err(emb, g["emb"]), O.rel_err(atp, g["atp"])
+    agree = argmax_agreement(atp, g["atp"])
+    print(f"[2DRB_1/{precision}] emb {e_emb:.3e} atp {e_atp:.3e} argmax {agree:.4f}")
+    tol = FP32_TOL if precision == "fp32" else BF16_TOL
+    assert e_emb < tol and e_atp < tol
+    assert agree >= 0.99
+    assert atp.min() >= 0 and atp.sum(-1).max() <= 1 + 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_layer_vs_reference_layer(pkg, golden_dir, precision):
+    """AxialTransformerLayer.forward against the top-level reference layer's vectors."""
+    g = np.load(os.path.join(golden_dir, "layer.npz"))
+    sd = O.make_weights(int(g["wseed"]), num_layers=1, sharpen=float(g["sharpen"]))
+    layer = pkg.AxialTransformerLayer(768, 3072, 12).set_precision(precision)
+    layer.load_state_dict({k[len("layers.0."):]: v for k, v in sd.items() if k.startswith("layers.0.")}, strict=True)
+    layer = layer.eval().cuda()
+    x = torch.from_numpy(g["x"]).cuda()
+    pad = torch.from_numpy(g["pad"]).cuda()
+    tol = FP32_TOL if precision == "fp32" else BF16_TOL
+    for tag, pm in (("nopad", None), ("pad", pad)):
+        y, col, row = layer(x, self_attn_padding_mask=pm, need_head_weights=True)
+        assert col is None and tuple(row.shape) == (12, 1, x.shape[1], x.shape[1])
+        e = (O.rel_err(y.cpu(), g[f"y_{tag}"]), O.rel_err(row.cpu(), g[f"row_{tag}"]))
+        print(f"[layer/{tag}/{precision}] x {e[0]:.3e} row {e[1]:.3e}")
+        assert max(e) < tol
+        y2 = layer(x, self_attn_padding_mask=pm)
+        assert torch.equal(y2, y)          # deterministic; same result without head weights
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_submodules_match_fused_layer(pkg, golden_dir, precision):
+    """Row / Column / FFN residual blocks called one by one == the fused layer driver."""
+    g = np.load(os.path.join(golden_dir, "layer.npz"))
+    sd = O.make_weights(int(g["wseed"]), num_layers=1, sharpen=float(g["sharpen"]))
+    layer = pkg.AxialTransformerLayer(768, 3072, 12).set_precision(precision)
+    layer.load_state_dict({k[len("layers.0."):]: v for k, v in sd.items() if k.startswith("layers.0.")}, strict=True)
+    layer = layer.eval().cuda()
+    x = torch.from_numpy(g["x"]).cuda()
+    pad = torch.from_numpy(g["pad"]).cuda()
+    y_fused, _, row_fused = layer(x, self_attn_padding_mask=pad, need_head_weights=True)
+    h, row = layer.row_self_attention(x, self_attn_padding_mask=pad)
+    h, col = layer.column_self_attention(h, self_attn_padding_mask=pad)
+    h = layer.feed_forward_layer(h)
+    tol = 1e-5 if precision == "fp32" else 1e-2     # bf16: the un-fused path rounds the block outputs to bf16
+    assert O.rel_err(row.cpu(), row_fused.cpu()) < tol
+    assert O.rel_err(h.cpu(), y_fused.cpu()) < tol
+    with pytest.raises(NotImplementedError):
+        layer.row_self_attention.layer(x, self_attn_mask=torch.ones(1, device="cuda"))
+
+
+def test_deep_msa_without_row_positions(pkg):
+    """R > 1024 is rejected with the row-position embedding (model.py:354-359) and accepted without
+    (BASELINE config 4 runs with embed_positions_msa=False); checked against the oracle at 2 layers."""
+    model, sd = build(pkg, 3, 2, 2.0, "fp32", embed_positions_msa=False)
+    tokens = O.make_tokens(1030, 6, 9)
+    ref = O.forward(sd, tokens, repr_layers=[2], need_head_weights=True, num_layers=2, want_logits=False)
+    out = model(tokens.cuda(), repr_layers=[2], need_head_weights=True, want_logits=False)
+    assert O.rel_err(out["representations"][2].cpu(), ref["representations"][2]) < FP32_TOL
+    assert O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"]) < FP32_TOL
+    model2, _ = build(pkg, 3, 1, 1.0, "fp32")
+    with pytest.raises(RuntimeError, match="1024"):
+        model2(tokens.cuda())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mid_size_vs_oracle(pkg, precision):
+    """A chunk-threshold-crossing shape (R*C > 16384) against the un-chunked oracle, 3 layers."""
+    model, sd = build(pkg, 42, 3, 4.0, precision)
+    tokens = O.make_tokens(96, 200, 8)
+    ref = O.forward(sd, tokens, repr_layers=[3], need_head_weights=True, num_layers=3, want_logits=False)
+    out = model(tokens.cuda(), repr_layers=[3], need_head_weights=True, want_logits=False)
+    e_rep = O.rel_err(out["representations"][3].cpu(), ref["representations"][3])
+    e_att = O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"])
+    agree = argmax_agreement(out["row_attentions"].cpu(), ref["row_attentions"])
+    print(f"[mid/{precision}] rep {e_rep:.3e} att {e_att:.3e} argmax {agree:.4f}")
+    tol = FP32_TOL if precision == "fp32" else BF16_TOL
+    assert e_rep < tol and e_att < tol
+    if precision == "bf16":
+        assert agree >= 0.99
+
+
+def test_contacts_and_api_surface(pkg):
+    model, sd = build(pkg, 1, 2, 3.0, "fp32")
+    tokens = O.make_tokens(5, 12, 3)
+    ref = O.forward(sd, tokens, need_head_weights=True, return_contacts=True, num_layers=2)
+    out = model(tokens.cuda(), return_contacts=True)
+    assert set(out) == {"logits", "representations", "row_attentions", "contacts"}
+    assert O.rel_err(out["contacts"].cpu(), ref["contacts"]) < 1e-3
+    assert tuple(model.predict_contacts(tokens.cuda()).shape) == (1, 11, 11)
+    assert tuple(model.get_sequence_attention(tokens).shape) == (1, 2, 12, 12, 12)
+    model.max_tokens_per_msa_(1 << 20)
+    with pytest.raises(AssertionError):
+        model(tokens[0].cuda())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(tokens)                    # CPU tensor: no fallback
+    model.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        model(tokens.cuda())

@@ -1,0 +1,211 @@
+"""GPU parity, per kernel group (K1..K9), through the C ABI.  The checker is the CPU oracle
+(oracle/msa_ref.py) or a float64 restatement of the single op on the same (already rounded) inputs.
+
+Tolerances (norm-relative, max|a-b| / max|b|):
+  fp32 path : 2e-5 per op (FFMA, fp32 accumulate; the whole-model gate is 1e-4)
+  bf16 path : inputs are rounded to bf16 first and the checker consumes the SAME rounded inputs, so
+              what remains is fp32-accumulation order plus one bf16 rounding of the output: 1e-2.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import msa_ref as O
+
+pytestmark = pytest.mark.gpu
+
+H, D = 12, 768
+
+
+@pytest.fixture(scope="module")
+def L():
+    from rnamsm_b200 import _lib
+    _lib.device_check(torch.device("cuda:0"))
+    return _lib
+
+
+def rel(a, b):
+    return O.rel_err(a.detach().double().cpu(), b.detach().double().cpu())
+
+
+def tol(code):
+    return 2e-5 if code == 0 else 1e-2
+
+
+def gen(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("R,C,pad_cols,pad_rows", [(5, 9, 0, 0), (8, 70, 3, 2), (3, 130, 0, 1), (33, 64, 64 - 1, 0)])
+def test_embed_layernorm(L, R, C, pad_cols, pad_rows):
+    sd = O.make_weights(3, num_layers=1)
+    tokens = O.make_tokens(R, C, 7, pad_cols=pad_cols, pad_rows=pad_rows)
+    # sprinkle pads in the middle of rows too: positions must skip them (modules.py:286-291)
+    if pad_cols or pad_rows:
+        tokens[0, 1, 2] = O.PAD_IDX
+    ref, pm = O.embed(sd, tokens)
+    dev = "cuda"
+    x = torch.empty(R * C, D, device=dev)
+    pad = torch.empty(R * C, dtype=torch.uint8, device=dev)
+    cu = {k: sd[k].to(dev) for k in ("embed_tokens.weight", "embed_positions.weight", "msa_position_embedding",
+                                      "emb_layer_norm_before.weight", "emb_layer_norm_before.bias")}
+    rp = cu["msa_position_embedding"].reshape(-1).contiguous()
+    L.check(L.lib.rnamsm_embed_layernorm(L.ptr(tokens[0].to(dev)), R, C, L.ptr(cu["embed_tokens.weight"]), O.VOCAB,
+                                         L.ptr(cu["embed_positions.weight"]), cu["embed_positions.weight"].shape[0],
+                                         L.ptr(rp), L.ptr(cu["emb_layer_norm_before.weight"]),
+                                         L.ptr(cu["emb_layer_norm_before.bias"]), D, O.PAD_IDX, O.LN_EPS, L.ptr(x),
+                                         L.ptr(pad), L.stream_ptr()))
+    assert rel(x.view(R, C, D), ref[0]) < 2e-6
+    want_pad = tokens[0].eq(O.PAD_IDX).reshape(-1).to(torch.uint8)
+    assert torch.equal(pad.cpu(), want_pad)
+    if pm is not None:
+        assert float(x.view(R, C, D)[tokens[0].eq(O.PAD_IDX).to(dev)].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("rows", [1, 7, 1000])
+@pytest.mark.parametrize("code", [0, 1], ids=["f32", "bf16"])
+def test_layernorm(L, rows, code):
+    x = gen((rows, D), 1, 3.0) + 0.5
+    w, b = 1 + 0.1 * gen((D,), 2), 0.1 * gen((D,), 3)
+    ref = O.layer_norm(x.double(), w.double(), b.double())
+    y = torch.empty(rows, D, dtype=L.torch_dtype(code), device="cuda")
+    L.check(L.lib.rnamsm_layernorm(L.ptr(x.cuda()), L.ptr(w.cuda()), L.ptr(b.cuda()), L.ptr(y), code, rows, D,
+                                   O.LN_EPS, L.stream_ptr()))
+    assert rel(y, ref) < (2e-6 if code == 0 else 5e-3)
+
+
+# ------------------------------------------------------------------------------------------ K3/K6/K8
+def run_linear(L, x, W, bias, code, epi, q_scale=1.0, q_cols=0, row_mask=None, out=None):
+    M, K = x.shape
+    N = W.shape[0]
+    dt = L.torch_dtype(code)
+    xd, Wd = x.to(dt).cuda(), W.to(dt).cuda()
+    if out is None:
+        out = torch.empty(M, N, dtype=dt, device="cuda")
+    L.check(L.lib.rnamsm_linear(L.ptr(xd), L.ptr(Wd), L.ptr(bias.cuda()), M, N, K, code, epi, q_scale, q_cols,
+                                L.ptr(row_mask), L.ptr(out), L.stream_ptr()))
+    return out, xd.double().cpu(), Wd.double().cpu()
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 768, 768), (100, 2304, 768), (128, 768, 768), (300, 768, 3072),
+                                   (1000, 3072, 768), (257, 768, 768)])
+@pytest.mark.parametrize("code", [0, 1], ids=["f32", "bf16"])
+def test_linear_bias_and_qscale(L, M, N, K, code):
+    x, W, bias = gen((M, K), 1), gen((N, K), 2, 0.05), gen((N,), 3, 0.1)
+    mask = (torch.rand(M, generator=torch.Generator().manual_seed(4)) < 0.2).to(torch.uint8)
+    q_cols = 768 if N == 2304 else 0
+    out, xr, Wr = run_linear(L, x, W, bias, code, 0, 0.37, q_cols, mask.cuda() if q_cols else None)
+    ref = xr @ Wr.T + bias.double()
+    if q_cols:
+        ref[:, :q_cols] *= 0.37
+        ref[mask.bool(), :q_cols] = 0
+    assert rel(out, ref) < tol(code)
+
+
+@pytest.mark.parametrize("M,N,K", [(130, 3072, 768), (64, 768, 768)])
+@pytest.mark.parametrize("code", [0, 1], ids=["f32", "bf16"])
+def test_linear_gelu(L, M, N, K, code):
+    x, W, bias = gen((M, K), 5), gen((N, K), 6, 0.08), gen((N,), 7, 0.1)
+    out, xr, Wr = run_linear(L, x, W, bias, code, 1)
+    ref = O.gelu_erf(xr @ Wr.T + bias.double())
+    assert rel(out, ref) < tol(code)
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 768, 3072), (129, 768, 768)])
+@pytest.mark.parametrize("code", [0, 1], ids=["f32", "bf16"])
+def test_linear_residual(L, M, N, K, code):
+    x, W, bias = gen((M, K), 8), gen((N, K), 9, 0.05), gen((N,), 10, 0.1)
+    resid = gen((M, N), 11)
+    out = resid.clone().cuda()
+    out, xr, Wr = run_linear(L, x, W, bias, code, 2, out=out)
+    ref = resid.double() + xr @ Wr.T + bias.double()
+    assert out.dtype == torch.float32
+    assert rel(out, ref) < (2e-5 if code == 0 else 1e-5)   # fp32 output in both modes
+
+
+# ------------------------------------------------------------------------------------------ K4/K5/K6
+def make_qkv(R, C, seed, code, L, scale=1.0):
+    dt = L.torch_dtype(code)
+    qkv = (gen((R, C, 3 * D), seed) * scale).to(dt).cuda()
+    return qkv, qkv.double().cpu()
+
+
+@pytest.mark.parametrize("R,C", [(4, 9), (7, 36), (33, 130), (64, 257), (20, 300)])
+@pytest.mark.parametrize("code", [0, 1], ids=["f32", "bf16"])
+def test_row_attention_chain(L, R, C, code):
+    """K4 (split-K tied logits) -> K5 (softmax + key mask) -> K6 (AV)."""
+    qkv, q64 = make_qkv(R, C, 21, code, L, 0.4)
+    q = q64[..., :D].view(R, C, H, 64)
+    k = q64[..., D:2 * D].view(R, C, H, 64)
+    v = q64[..., 2 * D:].view(R, C, H, 64)
+    logits_ref = torch.einsum("rihd,rjhd->hij", q, k)
+    for splits in sorted({1, L.lib.rnamsm_row_attn_splits(R, C, H, code), min(R, 3)}):
+        if (splits - 1) * math.ceil(R / splits) >= R:
+            continue
+        partial = torch.empty(splits, H, C, C, device="cuda")
+        L.check(L.lib.rnamsm_row_attn_logits(L.ptr(qkv), R, C, H, code, L.ptr(partial), splits, L.stream_ptr()))
+        assert rel(partial.sum(0), logits_ref) < 2e-5, f"splits={splits}"
+    key_pad = torch.zeros(C, dtype=torch.uint8)
+    key_pad[-2:] = 1
+    masked = logits_ref.float().masked_fill(key_pad.bool()[None, None, :], -10000)
+    probs_ref = masked.double().softmax(-1)
+    pmap = torch.empty(H, C, C, device="cuda")
+    ldp = (C + 7) // 8 * 8 if code == 1 else C
+    plp = torch.full((H, C, ldp), 7.0, dtype=L.torch_dtype(code), device="cuda") if code == 1 else None
+    L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), splits, H, C, L.ptr(key_pad.cuda()), L.ptr(pmap), L.ptr(plp), ldp,
+                                     code, L.stream_ptr()))
+    assert rel(pmap, probs_ref) < 2e-5
+    if plp is not None:
+        assert rel(plp[..., :C], probs_ref) < 5e-3
+        assert float(plp[..., C:].abs().sum()) == 0.0            # zero-filled padding columns
+    p_in = plp if plp is not None else pmap
+    ctx = torch.empty(R * C, D, dtype=L.torch_dtype(code), device="cuda")
+    L.check(L.lib.rnamsm_row_attn_av(L.ptr(p_in), ldp, L.ptr(qkv), R, C, H, code, L.ptr(ctx), L.stream_ptr()))
+    ctx_ref = torch.einsum("hij,rjhd->rihd", p_in[..., :C].double().cpu(), v).reshape(R * C, D)
+    assert rel(ctx, ctx_ref) < tol(code)
+
+
+# ------------------------------------------------------------------------------------------ K7
+@pytest.mark.parametrize("R,C,with_pad", [(2, 5, False), (9, 7, True), (64, 3, False), (65, 4, True), (130, 6, True),
+                                          (300, 2, False)])
+@pytest.mark.parametrize("code", [0, 1], ids=["f32", "bf16"])
+def test_column_attention(L, R, C, with_pad, code):
+    qkv, q64 = make_qkv(R, C, 31, code, L, 0.5)
+    q = q64[..., :D].view(R, C, H, 64)
+    k = q64[..., D:2 * D].view(R, C, H, 64)
+    v = q64[..., 2 * D:].view(R, C, H, 64)
+    att = torch.einsum("ichd,jchd->hcij", q, k)
+    pad = None
+    if with_pad:
+        pad = torch.zeros(R, C, dtype=torch.bool)
+        pad[-1, :] = True
+        pad[R // 2, 0] = True
+        pad[:, C - 1] = True                      # a fully padded column -> uniform attention
+        att = att.masked_fill(pad.T[None, :, None, :], -10000)
+    ctx_ref = torch.einsum("hcij,jchd->ichd", att.softmax(-1), v).reshape(R * C, D)
+    ctx = torch.empty(R * C, D, dtype=L.torch_dtype(code), device="cuda")
+    pad_u8 = pad.to(torch.uint8).cuda() if pad is not None else None
+    L.check(L.lib.rnamsm_col_attn(L.ptr(qkv), R, C, H, code, L.ptr(pad_u8), L.ptr(ctx), L.stream_ptr()))
+    assert rel(ctx, ctx_ref) < tol(code)
+
+
+# ------------------------------------------------------------------------------------------ K9b
+def test_vocab_proj(L):
+    h, E, b = gen((77, D), 1), gen((12, D), 2), gen((12,), 3)
+    out = torch.empty(77, 12, device="cuda")
+    L.check(L.lib.rnamsm_vocab_proj(L.ptr(h.cuda()), L.ptr(E.cuda()), L.ptr(b.cuda()), 77, 12, D, L.ptr(out),
+                                    L.stream_ptr()))
+    assert rel(out, h.double() @ E.double().T + b.double()) < 2e-6
+
+
+def test_error_paths(L):
+    x = torch.zeros(4, 100, device="cuda")
+    with pytest.raises(RuntimeError, match="multiple of 128"):
+        L.check(L.lib.rnamsm_layernorm(L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), 0, 4, 100, 1e-5, L.stream_ptr()), "ln")
+    with pytest.raises(RuntimeError, match="R=1"):
+        L.check(L.lib.rnamsm_col_attn(L.ptr(x), 1, 4, 12, 0, None, L.ptr(x), L.stream_ptr()), "col")
