@@ -155,7 +155,7 @@ def test_deep_msa_without_row_positions(pkg):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_mid_size_vs_oracle(pkg, precision):
     """A chunk-threshold-crossing shape (R*C > 16384) against the un-chunked oracle, 3 layers."""
-    model, sd = build(pkg, 42, 3, 4.0, precision)
+    model, sd = build(pkg, 42, 3, 3.0, precision)
     tokens = O.make_tokens(96, 200, 8)
     ref = O.forward(sd, tokens, repr_layers=[3], need_head_weights=True, num_layers=3, want_logits=False)
     out = model(tokens.cuda(), repr_layers=[3], need_head_weights=True, want_logits=False)

@@ -54,7 +54,8 @@ def test_embed_layernorm(L, R, C, pad_cols, pad_rows):
     cu = {k: sd[k].to(dev) for k in ("embed_tokens.weight", "embed_positions.weight", "msa_position_embedding",
                                       "emb_layer_norm_before.weight", "emb_layer_norm_before.bias")}
     rp = cu["msa_position_embedding"].reshape(-1).contiguous()
-    L.check(L.lib.rnamsm_embed_layernorm(L.ptr(tokens[0].to(dev)), R, C, L.ptr(cu["embed_tokens.weight"]), O.VOCAB,
+    tok_dev = tokens[0].to(dev)
+    L.check(L.lib.rnamsm_embed_layernorm(L.ptr(tok_dev), R, C, L.ptr(cu["embed_tokens.weight"]), O.VOCAB,
                                          L.ptr(cu["embed_positions.weight"]), cu["embed_positions.weight"].shape[0],
                                          L.ptr(rp), L.ptr(cu["emb_layer_norm_before.weight"]),
                                          L.ptr(cu["emb_layer_norm_before.bias"]), D, O.PAD_IDX, O.LN_EPS, L.ptr(x),
@@ -74,8 +75,8 @@ def test_layernorm(L, rows, code):
     w, b = 1 + 0.1 * gen((D,), 2), 0.1 * gen((D,), 3)
     ref = O.layer_norm(x.double(), w.double(), b.double())
     y = torch.empty(rows, D, dtype=L.torch_dtype(code), device="cuda")
-    L.check(L.lib.rnamsm_layernorm(L.ptr(x.cuda()), L.ptr(w.cuda()), L.ptr(b.cuda()), L.ptr(y), code, rows, D,
-                                   O.LN_EPS, L.stream_ptr()))
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()      # named: a temporary would be freed before the launch
+    L.check(L.lib.rnamsm_layernorm(L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(y), code, rows, D, O.LN_EPS, L.stream_ptr()))
     assert rel(y, ref) < (2e-6 if code == 0 else 5e-3)
 
 
@@ -84,10 +85,10 @@ def run_linear(L, x, W, bias, code, epi, q_scale=1.0, q_cols=0, row_mask=None, o
     M, K = x.shape
     N = W.shape[0]
     dt = L.torch_dtype(code)
-    xd, Wd = x.to(dt).cuda(), W.to(dt).cuda()
+    xd, Wd, bd = x.to(dt).cuda(), W.to(dt).cuda(), bias.cuda()
     if out is None:
         out = torch.empty(M, N, dtype=dt, device="cuda")
-    L.check(L.lib.rnamsm_linear(L.ptr(xd), L.ptr(Wd), L.ptr(bias.cuda()), M, N, K, code, epi, q_scale, q_cols,
+    L.check(L.lib.rnamsm_linear(L.ptr(xd), L.ptr(Wd), L.ptr(bd), M, N, K, code, epi, q_scale, q_cols,
                                 L.ptr(row_mask), L.ptr(out), L.stream_ptr()))
     return out, xd.double().cpu(), Wd.double().cpu()
 
@@ -144,9 +145,10 @@ def test_row_attention_chain(L, R, C, code):
     k = q64[..., D:2 * D].view(R, C, H, 64)
     v = q64[..., 2 * D:].view(R, C, H, 64)
     logits_ref = torch.einsum("rihd,rjhd->hij", q, k)
-    for splits in sorted({1, L.lib.rnamsm_row_attn_splits(R, C, H, code), min(R, 3)}):
-        if (splits - 1) * math.ceil(R / splits) >= R:
-            continue
+    for n_splits in sorted({1, L.lib.rnamsm_row_attn_splits(R, C, H, code), min(R, 3)}):
+        if (n_splits - 1) * math.ceil(R / n_splits) >= R:
+            continue                                   # would leave an empty split: rejected by the ABI
+        splits = n_splits
         partial = torch.empty(splits, H, C, C, device="cuda")
         L.check(L.lib.rnamsm_row_attn_logits(L.ptr(qkv), R, C, H, code, L.ptr(partial), splits, L.stream_ptr()))
         assert rel(partial.sum(0), logits_ref) < 2e-5, f"splits={splits}"
@@ -157,7 +159,8 @@ def test_row_attention_chain(L, R, C, code):
     pmap = torch.empty(H, C, C, device="cuda")
     ldp = (C + 7) // 8 * 8 if code == 1 else C
     plp = torch.full((H, C, ldp), 7.0, dtype=L.torch_dtype(code), device="cuda") if code == 1 else None
-    L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), splits, H, C, L.ptr(key_pad.cuda()), L.ptr(pmap), L.ptr(plp), ldp,
+    key_pad_dev = key_pad.cuda()
+    L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), splits, H, C, L.ptr(key_pad_dev), L.ptr(pmap), L.ptr(plp), ldp,
                                      code, L.stream_ptr()))
     assert rel(pmap, probs_ref) < 2e-5
     if plp is not None:
@@ -198,8 +201,8 @@ def test_column_attention(L, R, C, with_pad, code):
 def test_vocab_proj(L):
     h, E, b = gen((77, D), 1), gen((12, D), 2), gen((12,), 3)
     out = torch.empty(77, 12, device="cuda")
-    L.check(L.lib.rnamsm_vocab_proj(L.ptr(h.cuda()), L.ptr(E.cuda()), L.ptr(b.cuda()), 77, 12, D, L.ptr(out),
-                                    L.stream_ptr()))
+    hd, Ed, bd = h.cuda(), E.cuda(), b.cuda()
+    L.check(L.lib.rnamsm_vocab_proj(L.ptr(hd), L.ptr(Ed), L.ptr(bd), 77, 12, D, L.ptr(out), L.stream_ptr()))
     assert rel(out, h.double() @ E.double().T + b.double()) < 2e-6
 
 

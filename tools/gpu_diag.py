@@ -14,12 +14,12 @@ os.makedirs(OUT, exist_ok=True)
 PYTEST = [sys.executable, "-m", "pytest", "-q", "-x", "--timeout", "600", "-p", "no:cacheprovider", "-s"]
 SECTIONS = {
     "elementwise": PYTEST + ["tests/test_gpu_ops.py", "-k", "embed or layernorm or vocab or error"],
-    "ops_f32": PYTEST[:3] + PYTEST[4:] + ["tests/test_gpu_ops.py", "-k", "f32"],
-    "linear_bf16": PYTEST[:3] + PYTEST[4:] + ["tests/test_gpu_ops.py", "-k", "linear and bf16"],
-    "row_bf16": PYTEST[:3] + PYTEST[4:] + ["tests/test_gpu_ops.py", "-k", "row_attention and bf16"],
-    "col_bf16": PYTEST[:3] + PYTEST[4:] + ["tests/test_gpu_ops.py", "-k", "column_attention and bf16"],
-    "model_f32": PYTEST[:3] + PYTEST[4:] + ["tests/test_gpu_model.py", "-k", "fp32 or deep or contacts"],
-    "model_bf16": PYTEST[:3] + PYTEST[4:] + ["tests/test_gpu_model.py", "-k", "bf16"],
+    "ops_f32": PYTEST[:4] + PYTEST[5:] + ["tests/test_gpu_ops.py", "-k", "f32"],
+    "linear_bf16": PYTEST[:4] + PYTEST[5:] + ["tests/test_gpu_ops.py", "-k", "linear and bf16"],
+    "row_bf16": PYTEST[:4] + PYTEST[5:] + ["tests/test_gpu_ops.py", "-k", "row_attention and bf16"],
+    "col_bf16": PYTEST[:4] + PYTEST[5:] + ["tests/test_gpu_ops.py", "-k", "column_attention and bf16"],
+    "model_f32": PYTEST[:4] + PYTEST[5:] + ["tests/test_gpu_model.py", "-k", "fp32 or deep or contacts"],
+    "model_bf16": PYTEST[:4] + PYTEST[5:] + ["tests/test_gpu_model.py", "-k", "bf16"],
     "smoke": [sys.executable, "__graft_entry__.py", "smoke"],
     "bench_cfg2": [sys.executable, "bench.py", "--steps", "5", "--warmup", "3"],
     "bench_cfg2_f32": [sys.executable, "bench.py", "--steps", "2", "--warmup", "1", "--precision", "fp32"],
