@@ -17,9 +17,14 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
  *   - return value 0 = ok; non-zero = error, message in rnamsm_last_error() (thread-local);
  *   - `dtype` selects the arithmetic path: RNAMSM_F32 = fp32 FFMA kernels (parity path,
- *     <=1e-4 norm-relative vs the reference fp32 forward), RNAMSM_BF16 = bf16 operands on the
- *     tcgen05 tensor cores with fp32 accumulation, fp32 residual stream / LayerNorm / softmax
- *     (<=2e-2).  There is no CPU fallback.
+ *     <=1e-4 norm-relative vs the reference fp32 forward); RNAMSM_BF16 / RNAMSM_F16 = 16-bit
+ *     operands on the tcgen05 tensor cores (kind::f16, same rate for both element types) with
+ *     fp32 accumulation and an fp32 residual stream / LayerNorm / softmax (<=2e-2).  In the
+ *     whole-layer drivers each attention block carries its own operand type
+ *     (rnamsm_attn_weights.dtype): the production "bf16" path runs the tied row-attention block
+ *     in fp16 -- its logits are sums over R*64 products whose rounding errors add coherently on
+ *     redundant MSAs, and fp16's three extra mantissa bits bring the exported maps from 4.5e-2
+ *     to <1e-2 on the 2DRB_1 MSA at no cost in speed.  There is no CPU fallback.
  *   - one MSA per call (B = 1): the reference never batches MSAs (RNA_MSM_Inference.py:147)
  *     and its tied-attention scaling depends on the padded row count (modules.py:713-715).
  *   - activations are token-major: x[(r*C + c)*D + f], i.e. the reference's [R,C,B=1,D].
@@ -34,9 +39,9 @@
 extern "C" {
 #endif
 
-#define RNAMSM_ABI_VERSION 1
+#define RNAMSM_ABI_VERSION 2
 
-enum { RNAMSM_F32 = 0, RNAMSM_BF16 = 1 };
+enum { RNAMSM_F32 = 0, RNAMSM_BF16 = 1, RNAMSM_F16 = 2 };
 
 /* Epilogues of rnamsm_linear. */
 enum {
@@ -51,6 +56,11 @@ const char* rnamsm_last_error(void);
 int rnamsm_device_check(void);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 long long rnamsm_launch_count(void);
+
+/* CTA pairs (clusters of 2) the persistent tcgen05 GEMM grid uses on this device: the number
+ * that can be co-resident (cudaOccupancyMaxActiveClusters), known after the first 16-bit launch;
+ * 0 before. */
+int rnamsm_gemm_pairs(void);
 
 /* Optional device timing of every kernel launch by class (cudaEvents recorded on the launching
  * stream around each launch).  enable(1) resets and starts recording, enable(0) stops;
@@ -92,11 +102,12 @@ int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, floa
 /* Suggested split count for K4 so that the launch fills the 148 SMs. */
 int rnamsm_row_attn_splits(int R, int C, int H, int dtype);
 
-/* K5 -- sum the split partials, mask keys (logit = -10000 where key_pad[j], modules.py:780-784),
- * softmax over j (modules.py:818).  probs_out fp32 [H,C,C] is the exported attention map
+/* K5 -- sum the split partials, multiply by logit_scale (1 when q already carries the whole
+ * align_scaling; 1/sqrt(R) in the 16-bit path where q carries only 64^-1/2), mask keys
+ * (logit = -10000 where key_pad[j], modules.py:780-784), softmax over j (modules.py:818).  probs_out fp32 [H,C,C] is the exported attention map
  * (written straight into the caller's [N,H,C,C] slab); probs_lp ([H,C,ld_lp] in `dtype`, columns
  * >= C zero-filled) feeds K6 and may be NULL in fp32 mode where K6 reads probs_out. */
-int rnamsm_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad,
+int rnamsm_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float logit_scale,
                        float* probs_out, void* probs_lp, int ld_lp, int dtype, void* stream);
 
 /* K6 -- ctx[r,i,h,:] = sum_j P[h,i,j] v[r,j,h,:] (modules.py:797).  probs [H,C,ldp] in `dtype`;
@@ -123,6 +134,9 @@ typedef struct rnamsm_attn_weights {
   const float* b_qkv; /* [3D] */
   const void* w_out; /* [D, D] compute dtype */
   const float* b_out; /* [D] */
+  int dtype;          /* operand type of w_qkv / w_out and of this block's arithmetic: RNAMSM_BF16 or
+                         RNAMSM_F16 in the 16-bit path (0 = same as the call's dtype); ignored (fp32)
+                         when the call's dtype is RNAMSM_F32 */
 } rnamsm_attn_weights;
 
 typedef struct rnamsm_layer_weights {

@@ -14,14 +14,15 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "librnamsm_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 
 _vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 
 
 class AttnWeights(C.Structure):
-    _fields_ = [("ln_w", _vp), ("ln_b", _vp), ("w_qkv", _vp), ("b_qkv", _vp), ("w_out", _vp), ("b_out", _vp)]
+    _fields_ = [("ln_w", _vp), ("ln_b", _vp), ("w_qkv", _vp), ("b_qkv", _vp), ("w_out", _vp), ("b_out", _vp),
+                ("dtype", _i)]
 
 
 class LayerWeights(C.Structure):
@@ -44,6 +45,7 @@ SIGNATURES = {
     "rnamsm_last_error": (C.c_char_p, []),
     "rnamsm_device_check": (_i, []),
     "rnamsm_launch_count": (_ll, []),
+    "rnamsm_gemm_pairs": (_i, []),
     "rnamsm_profile_enable": (_i, [_i]),
     "rnamsm_profile_num_classes": (_i, []),
     "rnamsm_profile_class_name": (C.c_char_p, [_i]),
@@ -53,7 +55,7 @@ SIGNATURES = {
     "rnamsm_linear": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "rnamsm_row_attn_logits": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "rnamsm_row_attn_splits": (_i, [_i, _i, _i, _i]),
-    "rnamsm_row_softmax": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "rnamsm_row_softmax": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _i, _i, _vp]),
     "rnamsm_row_attn_av": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "rnamsm_col_attn": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnamsm_vocab_proj": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
@@ -74,7 +76,8 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-assert lib.rnamsm_version() == 1, "librnamsm_b200.so ABI version mismatch"
+ABI_VERSION = 2
+assert lib.rnamsm_version() == ABI_VERSION, "librnamsm_b200.so ABI version mismatch"
 
 
 def check(rc: int, what: str = "") -> None:
@@ -112,15 +115,27 @@ def device_check(device: torch.device) -> None:
 
 
 def dtype_code(precision: str) -> int:
-    if precision in ("bf16", "bfloat16"):
+    if precision in ("bf16", "bfloat16", "bf16_pure"):
         return BF16
+    if precision in ("fp16", "float16", "f16"):
+        return F16
     if precision in ("fp32", "float32", "f32"):
         return F32
-    raise ValueError(f"unknown precision {precision!r} (expected 'bf16' or 'fp32')")
+    raise ValueError(f"unknown precision {precision!r} (expected 'bf16', 'bf16_pure', 'fp16' or 'fp32')")
+
+
+def row_dtype_code(precision: str) -> int:
+    """Operand type of the tied row-attention block.  The production 'bf16' path runs it in fp16
+    (same tensor-core rate, 3 more mantissa bits: the tied logits are sums of R*64 products and
+    feed the exported maps); 'bf16_pure' keeps bf16 there too (RNAMSM_ROW_ATTN_FP16=0 does the same)."""
+    code = dtype_code(precision)
+    if code == BF16 and precision != "bf16_pure" and os.environ.get("RNAMSM_ROW_ATTN_FP16", "1") != "0":
+        return F16
+    return code
 
 
 def torch_dtype(code: int) -> torch.dtype:
-    return torch.bfloat16 if code == BF16 else torch.float32
+    return {BF16: torch.bfloat16, F16: torch.float16}.get(code, torch.float32)
 
 
 def profile_enable(on: bool) -> None:

@@ -55,8 +55,8 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof_events[reinterpret_cast<size_t>(slot) - 1].b, st);
 }
 
-int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box) {
+int encode_tmap(CUtensorMap* map, int elem, const void* base, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -88,7 +88,9 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
       }
     }
   }
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+  const CUtensorMapDataType dt = elem == TMAP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : elem == TMAP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = encode(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -116,8 +118,10 @@ struct Plan {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static inline bool is16(int dtype) { return dtype == RNAMSM_BF16 || dtype == RNAMSM_F16; }
+
 static int pick_splits(int R, int C, int H, int dtype) {
-  if (dtype == RNAMSM_BF16) return row_logits_splits_bf16(R, C, H);
+  if (is16(dtype)) return row_logits_splits_16(R, C, H);
   const long long tiles = (long long)H * ceil_div(C, 128) * ceil_div(C, 128);
   int want = (int)std::max<long long>(1, (2 * 148) / std::max<long long>(1, tiles));
   want = std::max(1, std::min(want, std::max(1, R / 4)));
@@ -128,14 +132,14 @@ static int pick_splits(int R, int C, int H, int dtype) {
 static Plan make_plan(int R, int C, int D, int H, int F, int dtype) {
   Plan p{};
   const size_t T = (size_t)R * C;
-  p.el = dtype == RNAMSM_BF16 ? 2 : 4;
+  p.el = is16(dtype) ? 2 : 4;
   p.splits = pick_splits(R, C, H, dtype);
-  p.ldp = dtype == RNAMSM_BF16 ? (C + 7) / 8 * 8 : C;
+  p.ldp = is16(dtype) ? (C + 7) / 8 * 8 : C;
   size_t o = 0;
   p.off_xn = o;      o += align256(T * D * p.el);
   p.off_qkvh = o;    o += align256(T * (size_t)std::max(4 * D, F) * p.el);
   p.off_partial = o; o += align256((size_t)p.splits * H * C * C * 4);
-  p.off_probs = o;   o += align256(dtype == RNAMSM_BF16 ? (size_t)H * C * p.ldp * p.el : 0);
+  p.off_probs = o;   o += align256(is16(dtype) ? (size_t)H * C * p.ldp * p.el : 0);
   p.off_map = o;     o += align256((size_t)H * C * C * 4);
   p.total = o;
   return p;
@@ -143,11 +147,17 @@ static Plan make_plan(int R, int C, int D, int H, int F, int dtype) {
 
 static int linear_any(const void* x, const void* W, long long M, int N, int K, int dtype, const LinearEpilogue& e,
                       void* out, cudaStream_t st) {
-  if (dtype == RNAMSM_BF16) return launch_linear_bf16(x, W, M, N, K, e, out, st);
+  if (is16(dtype)) return launch_linear_16(x, W, M, N, K, dtype == RNAMSM_F16, e, out, st);
   if (dtype == RNAMSM_F32)
     return launch_linear_f32((const float*)x, (const float*)W, M, N, K, e, (float*)out, st);
   set_error("unknown dtype %d", dtype);
   return 2;
+}
+
+static int block_dtype(int requested, int dtype) {
+  // per-block operand type: 0 (unset) inherits the layer dtype; the fp32 path is all-fp32
+  if (dtype == RNAMSM_F32) return RNAMSM_F32;
+  return is16(requested) ? requested : dtype;
 }
 
 static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, float eps, float* x, int R, int C,
@@ -158,53 +168,59 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   uint8_t* qkv = ws + p.off_qkvh;
   void* ctx = qkv + (size_t)T * 3 * D * p.el;
   float* partial = reinterpret_cast<float*>(ws + p.off_partial);
-  void* probs_lp = dtype == RNAMSM_BF16 ? (void*)(ws + p.off_probs) : nullptr;
   float* map = row_probs_out ? row_probs_out : reinterpret_cast<float*>(ws + p.off_map);
+  const int row_dt = block_dtype(w->row.dtype, dtype);   // tied row attention: fp16 by default in the 16-bit path
+  const int col_dt = block_dtype(w->col.dtype, dtype);
+  void* probs_lp = is16(row_dt) ? (void*)(ws + p.off_probs) : nullptr;
   int rc;
 
   // ---- tied row attention: x += out_proj(AV(softmax(sum_r q k^T)))   modules.py:385-401, 802-821
-  if ((rc = launch_layernorm(x, w->row.ln_w, w->row.ln_b, xn, dtype, T, D, eps, st))) return rc;
+  if ((rc = launch_layernorm(x, w->row.ln_w, w->row.ln_b, xn, row_dt, T, D, eps, st))) return rc;
+  // align_scaling (modules.py:713-715) = 64^-1/2 / sqrt(R).  fp32 path: applied to q as the reference
+  // does.  16-bit path: q carries the exact power of two 64^-1/2 and the 1/sqrt(R) factor is applied
+  // to the fp32 logit sums in the softmax kernel (keeps q well inside the 16-bit normal range).
+  const float q_scale = is16(row_dt) ? 0.125f : 0.125f / sqrtf((float)R);
+  const float logit_scale = is16(row_dt) ? 1.0f / sqrtf((float)R) : 1.0f;
   {
-    const float scaling = (1.0f / sqrtf(64.f)) / sqrtf((float)R);  // align_scaling, modules.py:713-715
-    LinearEpilogue e{RNAMSM_EPI_BIAS, w->row.b_qkv, scaling, D, pad};
-    if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, dtype, e, qkv, st))) return rc;
+    LinearEpilogue e{RNAMSM_EPI_BIAS, w->row.b_qkv, q_scale, D, pad};
+    if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, row_dt, e, qkv, st))) return rc;
   }
-  if (dtype == RNAMSM_BF16) {
-    if ((rc = launch_row_logits_bf16(qkv, R, C, H, partial, p.splits, st))) return rc;
+  if (is16(row_dt)) {
+    if ((rc = launch_row_logits_16(qkv, R, C, H, row_dt == RNAMSM_F16, partial, p.splits, st))) return rc;
   } else {
     if ((rc = launch_row_logits_f32((const float*)qkv, R, C, H, partial, p.splits, st))) return rc;
   }
   // key mask comes from MSA row 0 (padding_mask[:, 0], modules.py:780-784) = first C entries of pad
-  if ((rc = launch_row_softmax(partial, p.splits, H, C, pad, map, probs_lp, p.ldp, dtype, st))) return rc;
-  if (dtype == RNAMSM_BF16) {
-    if ((rc = launch_row_av_bf16(probs_lp, p.ldp, qkv, R, C, H, ctx, st))) return rc;
+  if ((rc = launch_row_softmax(partial, p.splits, H, C, pad, logit_scale, map, probs_lp, p.ldp, row_dt, st))) return rc;
+  if (is16(row_dt)) {
+    if ((rc = launch_row_av_16(probs_lp, p.ldp, qkv, R, C, H, row_dt == RNAMSM_F16, ctx, st))) return rc;
   } else {
     if ((rc = launch_row_av_f32(map, C, (const float*)qkv, R, C, H, (float*)ctx, st))) return rc;
   }
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->row.b_out, 1.f, 0, nullptr};
-    if ((rc = linear_any(ctx, w->row.w_out, T, D, D, dtype, e, x, st))) return rc;
+    if ((rc = linear_any(ctx, w->row.w_out, T, D, D, row_dt, e, x, st))) return rc;
   }
 
   // ---- column attention over the MSA depth                           modules.py:875-945
-  if ((rc = launch_layernorm(x, w->col.ln_w, w->col.ln_b, xn, dtype, T, D, eps, st))) return rc;
+  if ((rc = launch_layernorm(x, w->col.ln_w, w->col.ln_b, xn, col_dt, T, D, eps, st))) return rc;
   if (R == 1) {
     // single-row shortcut: out_proj(v_proj(x)), modules.py:882-894.  Project with the v rows only.
     LinearEpilogue ev{RNAMSM_EPI_BIAS, w->col.b_qkv + 2 * D, 1.f, 0, nullptr};
     const void* wv = (const uint8_t*)w->col.w_qkv + (size_t)2 * D * D * p.el;
-    if ((rc = linear_any(xn, wv, T, D, D, dtype, ev, ctx, st))) return rc;
+    if ((rc = linear_any(xn, wv, T, D, D, col_dt, ev, ctx, st))) return rc;
   } else {
     LinearEpilogue e{RNAMSM_EPI_BIAS, w->col.b_qkv, 1.0f / sqrtf(64.f), D, nullptr};  // q *= scaling, :905
-    if ((rc = linear_any(xn, w->col.w_qkv, T, 3 * D, D, dtype, e, qkv, st))) return rc;
-    if (dtype == RNAMSM_BF16) {
-      if ((rc = launch_col_attn_bf16(qkv, R, C, H, pad, ctx, st))) return rc;
+    if ((rc = linear_any(xn, w->col.w_qkv, T, 3 * D, D, col_dt, e, qkv, st))) return rc;
+    if (is16(col_dt)) {
+      if ((rc = launch_col_attn_16(qkv, R, C, H, col_dt == RNAMSM_F16, pad, ctx, st))) return rc;
     } else {
       if ((rc = launch_col_attn_f32((const float*)qkv, R, C, H, pad, (float*)ctx, st))) return rc;
     }
   }
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->col.b_out, 1.f, 0, nullptr};
-    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, dtype, e, x, st))) return rc;
+    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st))) return rc;
   }
 
   // ---- feed-forward: x += fc2(gelu(fc1(LN(x))))                        modules.py:423-427
@@ -229,6 +245,7 @@ extern "C" {
 int rnamsm_version(void) { return RNAMSM_ABI_VERSION; }
 const char* rnamsm_last_error(void) { return get_error(); }
 long long rnamsm_launch_count(void) { return launch_count(); }
+int rnamsm_gemm_pairs(void) { return gemm_max_pairs(); }
 
 int rnamsm_profile_enable(int on) {
   for (auto& ev : g_prof_events) { g_prof_pool.push_back(ev.a); g_prof_pool.push_back(ev.b); }
@@ -286,24 +303,25 @@ int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, 
 int rnamsm_row_attn_splits(int R, int C, int H, int dtype) { return pick_splits(R, C, H, dtype); }
 
 int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, float* partial, int n_splits, void* stream) {
-  if (dtype == RNAMSM_BF16) return launch_row_logits_bf16(qkv, R, C, H, partial, n_splits, (cudaStream_t)stream);
+  if (is16(dtype)) return launch_row_logits_16(qkv, R, C, H, dtype == RNAMSM_F16, partial, n_splits, (cudaStream_t)stream);
   return launch_row_logits_f32((const float*)qkv, R, C, H, partial, n_splits, (cudaStream_t)stream);
 }
 
-int rnamsm_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float* probs_out,
-                       void* probs_lp, int ld_lp, int dtype, void* stream) {
-  return launch_row_softmax(partial, n_splits, H, C, key_pad, probs_out, probs_lp, ld_lp, dtype, (cudaStream_t)stream);
+int rnamsm_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float logit_scale,
+                       float* probs_out, void* probs_lp, int ld_lp, int dtype, void* stream) {
+  return launch_row_softmax(partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp, dtype,
+                            (cudaStream_t)stream);
 }
 
 int rnamsm_row_attn_av(const void* probs, int ldp, const void* qkv, int R, int C, int H, int dtype, void* ctx,
                        void* stream) {
-  if (dtype == RNAMSM_BF16) return launch_row_av_bf16(probs, ldp, qkv, R, C, H, ctx, (cudaStream_t)stream);
+  if (is16(dtype)) return launch_row_av_16(probs, ldp, qkv, R, C, H, dtype == RNAMSM_F16, ctx, (cudaStream_t)stream);
   return launch_row_av_f32((const float*)probs, ldp, (const float*)qkv, R, C, H, (float*)ctx, (cudaStream_t)stream);
 }
 
 int rnamsm_col_attn(const void* qkv, int R, int C, int H, int dtype, const uint8_t* pad, void* ctx, void* stream) {
   RNAMSM_REQUIRE(R >= 2, "rnamsm_col_attn: R=%d (the R == 1 shortcut is out_proj(v_proj(x)))", R);
-  if (dtype == RNAMSM_BF16) return launch_col_attn_bf16(qkv, R, C, H, pad, ctx, (cudaStream_t)stream);
+  if (is16(dtype)) return launch_col_attn_16(qkv, R, C, H, dtype == RNAMSM_F16, pad, ctx, (cudaStream_t)stream);
   return launch_col_attn_f32((const float*)qkv, R, C, H, pad, (float*)ctx, (cudaStream_t)stream);
 }
 
@@ -321,7 +339,7 @@ int rnamsm_layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
                          const uint8_t* pad, int dtype, float* row_probs_out, void* workspace, size_t workspace_bytes,
                          void* stream) {
   RNAMSM_REQUIRE(D == H * 64, "layer_forward: head_dim must be 64 (D=%d H=%d)", D, H);
-  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || dtype == RNAMSM_BF16, "layer_forward: unknown dtype %d", dtype);
+  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || is16(dtype), "layer_forward: unknown dtype %d", dtype);
   const Plan p = make_plan(R, C, D, H, F, dtype);
   RNAMSM_REQUIRE(workspace_bytes >= p.total, "layer_forward: workspace %zu < required %zu", workspace_bytes, p.total);
   RNAMSM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "layer_forward: workspace must be 256 B aligned");
@@ -335,7 +353,7 @@ int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int
   cudaStream_t st = (cudaStream_t)stream;
   const int D = m->embed_dim, H = m->num_heads, F = m->ffn_dim, N = m->num_layers;
   RNAMSM_REQUIRE(D == H * 64, "msa_forward: head_dim must be 64 (D=%d H=%d)", D, H);
-  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || dtype == RNAMSM_BF16, "msa_forward: unknown dtype %d", dtype);
+  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || is16(dtype), "msa_forward: unknown dtype %d", dtype);
   RNAMSM_REQUIRE(R >= 1 && C >= 1, "msa_forward: empty MSA (R=%d C=%d)", R, C);
   const Plan p = make_plan(R, C, D, H, F, dtype);
   const size_t T = (size_t)R * C;

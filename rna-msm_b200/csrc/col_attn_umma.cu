@@ -36,7 +36,7 @@ __device__ __forceinline__ float ex2(float x) {
 
 __global__ void __launch_bounds__(128)
 col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int R, int C,
-                     int H, const uint8_t* __restrict__ pad, __nv_bfloat16* __restrict__ ctx) {
+                     int H, int fp16, const uint8_t* __restrict__ pad, uint16_t* __restrict__ ctx) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
@@ -76,8 +76,8 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + BKV;
 
-  constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
-  constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);   // P (K-major) x V (MN-major)
+  const uint32_t idesc_s = make_idesc_16(BQ, BKV, fp16, 0, 0);  // Q (K-major) x K (K-major)
+  const uint32_t idesc_o = make_idesc_16(BQ, HD, fp16, 0, 1);   // P (K-major) x V (MN-major)
 
   auto load_kv = [&](int jb) {
     const int b = jb & 1;
@@ -163,7 +163,7 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const float p0 = ex2(fmaf(s[j], kLog2e, -mscaled));
       const float p1 = ex2(fmaf(s[j + 1], kLog2e, -mscaled));
       psum += p0 + p1;
-      pk[j >> 1] = pack_bf16(p0, p1);
+      pk[j >> 1] = fp16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
     }
     l_run = l_run * corr + psum;
     m_run = m_new;
@@ -205,11 +205,16 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int i = i0 + row;
   if (i < R) {
     const float inv = 1.f / l_run;
-    __nv_bfloat16* dst = ctx + ((size_t)i * C + c) * D + h * HD;
+    uint16_t* dst = ctx + ((size_t)i * C + c) * D + h * HD;
 #pragma unroll
     for (int d = 0; d < HD; d += 8) {
-      uint4 val = make_uint4(pack_bf16(o[d] * inv, o[d + 1] * inv), pack_bf16(o[d + 2] * inv, o[d + 3] * inv),
-                             pack_bf16(o[d + 4] * inv, o[d + 5] * inv), pack_bf16(o[d + 6] * inv, o[d + 7] * inv));
+      uint4 val;
+      if (fp16)
+        val = make_uint4(pack_f16(o[d] * inv, o[d + 1] * inv), pack_f16(o[d + 2] * inv, o[d + 3] * inv),
+                         pack_f16(o[d + 4] * inv, o[d + 5] * inv), pack_f16(o[d + 6] * inv, o[d + 7] * inv));
+      else
+        val = make_uint4(pack_bf16(o[d] * inv, o[d + 1] * inv), pack_bf16(o[d + 2] * inv, o[d + 3] * inv),
+                         pack_bf16(o[d + 4] * inv, o[d + 5] * inv), pack_bf16(o[d + 6] * inv, o[d + 7] * inv));
       *reinterpret_cast<uint4*>(dst + d) = val;
     }
   }
@@ -220,7 +225,7 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 }  // namespace
 
-int launch_col_attn_bf16(const void* qkv, int R, int C, int H, const uint8_t* pad, void* ctx, cudaStream_t st) {
+int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, const uint8_t* pad, void* ctx, cudaStream_t st) {
   RNAMSM_REQUIRE(R >= 1 && C >= 1 && H >= 1 && C <= 2147483647 / 1 && H <= 65535, "col_attn_bf16: bad shape");
   const int ld = 3 * H * HD;
   CUtensorMap tq, tkv;
@@ -228,13 +233,14 @@ int launch_col_attn_bf16(const void* qkv, int R, int C, int H, const uint8_t* pa
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)C * ld * 2};
   uint32_t box_q[3] = {HD, 1, BQ};
   uint32_t box_kv[3] = {HD, 1, BKV};
-  if (encode_tmap_bf16(&tq, qkv, 3, dims, strides, box_q)) return 3;
-  if (encode_tmap_bf16(&tkv, qkv, 3, dims, strides, box_kv)) return 3;
+  const int in_dt = fp16 ? TMAP_F16 : TMAP_BF16;
+  if (encode_tmap(&tq, in_dt, qkv, 3, dims, strides, box_q)) return 3;
+  if (encode_tmap(&tkv, in_dt, qkv, 3, dims, strides, box_kv)) return 3;
   RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   dim3 grid(C, H, ceil_div(R, BQ));
   RNAMSM_REQUIRE(grid.z <= 65535, "col_attn_bf16: R too large");
   ProfScope prof(KC_COL_ATTN, st);
-  col_attn_umma_kernel<<<grid, 128, kSmem, st>>>(tq, tkv, R, C, H, pad, reinterpret_cast<__nv_bfloat16*>(ctx));
+  col_attn_umma_kernel<<<grid, 128, kSmem, st>>>(tq, tkv, R, C, H, fp16, pad, reinterpret_cast<uint16_t*>(ctx));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

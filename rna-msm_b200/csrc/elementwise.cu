@@ -113,7 +113,8 @@ embed_ln_kernel(const int64_t* __restrict__ tokens, int R, int C, const float* _
 // -------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 8;
 
-template <bool kOutBf16>
+// kOut: 0 = fp32, 1 = bf16, 2 = fp16
+template <int kOut>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_kernel(const float* x, const float* __restrict__ w, const float* __restrict__ b,
                  void* y, long long n_rows, int D, float eps) {  // x may alias y (in-place final LN)
@@ -127,12 +128,13 @@ layernorm_kernel(const float* x, const float* __restrict__ w, const float* __res
     for (int i = 0; i < kMaxVec; ++i)
       if (i < nv) v[i] = *reinterpret_cast<const float4*>(src + lane * 4 + i * 128);
     warp_layernorm(v, nv, D, eps, w, b, lane);
-    if constexpr (kOutBf16) {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + (size_t)row * D;
+    if constexpr (kOut != 0) {
+      uint16_t* dst = reinterpret_cast<uint16_t*>(y) + (size_t)row * D;
 #pragma unroll
       for (int i = 0; i < kMaxVec; ++i)
         if (i < nv) {
-          uint2 pk = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+          uint2 pk = kOut == 1 ? make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w))
+                               : make_uint2(pack_f16(v[i].x, v[i].y), pack_f16(v[i].z, v[i].w));
           *reinterpret_cast<uint2*>(dst + lane * 4 + i * 128) = pk;
         }
     } else {
@@ -152,11 +154,14 @@ layernorm_kernel(const float* x, const float* __restrict__ w, const float* __res
 // -------------------------------------------------------------------------------------------
 constexpr int kSmWarps = 4;
 
-template <bool kLpBf16>
+// kLp: element type of the low-precision copy (0 = fp32, 1 = bf16, 2 = fp16).  logit_scale multiplies
+// the summed logits before the mask: the 16-bit path keeps q at 64^-1/2 scale (an exact power of
+// two) in 16 bits and applies the 1/sqrt(R) of align_scaling (modules.py:713-715) here in fp32.
+template <int kLp>
 __global__ void __launch_bounds__(kSmWarps * 32)
 row_softmax_kernel(const float* __restrict__ partial, int n_splits, int H, int C,
-                   const uint8_t* __restrict__ key_pad, float* __restrict__ probs_out, void* __restrict__ probs_lp,
-                   int ld_lp) {
+                   const uint8_t* __restrict__ key_pad, float logit_scale, float* __restrict__ probs_out,
+                   void* __restrict__ probs_lp, int ld_lp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kSmWarps + warp;  // h * C + i
   if (row >= (long long)H * C) return;
@@ -165,6 +170,7 @@ row_softmax_kernel(const float* __restrict__ partial, int n_splits, int H, int C
   auto logit = [&](int j) -> float {
     float a = 0.f;
     for (int s = 0; s < n_splits; ++s) a += src[s * split_stride + j];
+    a *= logit_scale;
     if (key_pad && key_pad[j]) a = -10000.f;  // masked_fill, modules.py:780-784
     return a;
   };
@@ -180,8 +186,10 @@ row_softmax_kernel(const float* __restrict__ partial, int n_splits, int H, int C
     const float p = (j < C) ? __expf(logit(j) - mx) * inv : 0.f;
     if (j < C) dst[j] = p;
     if (probs_lp && j < ld_lp) {
-      if constexpr (kLpBf16)
+      if constexpr (kLp == 1)
         reinterpret_cast<__nv_bfloat16*>(probs_lp)[(size_t)row * ld_lp + j] = __float2bfloat16(p);
+      else if constexpr (kLp == 2)
+        reinterpret_cast<__half*>(probs_lp)[(size_t)row * ld_lp + j] = __float2half_rn(p);
       else
         reinterpret_cast<float*>(probs_lp)[(size_t)row * ld_lp + j] = p;
     }
@@ -241,25 +249,29 @@ int launch_layernorm(const float* x, const float* w, const float* b, void* y, in
   const int blocks = (int)std::min<long long>((n_rows + kLnWarps - 1) / kLnWarps, 148LL * 32);
   ProfScope prof(KC_LAYERNORM, st);
   if (y_dtype == 1)
-    layernorm_kernel<true><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
+    layernorm_kernel<1><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
+  else if (y_dtype == 2)
+    layernorm_kernel<2><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
   else
-    layernorm_kernel<false><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
+    layernorm_kernel<0><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float* probs_out,
-                       void* probs_lp, int ld_lp, int dtype, cudaStream_t st) {
+int launch_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float logit_scale,
+                       float* probs_out, void* probs_lp, int ld_lp, int dtype, cudaStream_t st) {
   RNAMSM_REQUIRE(n_splits >= 1 && H > 0 && C > 0, "row_softmax: bad shape");
   const long long rows = (long long)H * C;
   const int blocks = (int)((rows + kSmWarps - 1) / kSmWarps);
   if (probs_lp == nullptr) ld_lp = 0;
   ProfScope prof(KC_ROW_SOFTMAX, st);
   if (dtype == 1)
-    row_softmax_kernel<true><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, probs_out, probs_lp, ld_lp);
+    row_softmax_kernel<1><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp);
+  else if (dtype == 2)
+    row_softmax_kernel<2><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp);
   else
-    row_softmax_kernel<false><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, probs_out, probs_lp, ld_lp);
+    row_softmax_kernel<0><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -30,8 +30,8 @@ int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, i
                     float eps, float* x_out, uint8_t* pad_out, cudaStream_t st);
 int launch_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
                      float eps, cudaStream_t st);
-int launch_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float* probs_out,
-                       void* probs_lp, int ld_lp, int dtype, cudaStream_t st);
+int launch_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float logit_scale,
+                       float* probs_out, void* probs_lp, int ld_lp, int dtype, cudaStream_t st);
 int launch_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
                       cudaStream_t st);
 
@@ -58,14 +58,16 @@ int launch_row_logits_f32(const float* qkv, int R, int C, int H, float* partial,
 int launch_row_av_f32(const float* probs, int ldp, const float* qkv, int R, int C, int H, float* ctx, cudaStream_t st);
 int launch_col_attn_f32(const float* qkv, int R, int C, int H, const uint8_t* pad, float* ctx, cudaStream_t st);
 
-// umma_gemm.cu -- bf16 tcgen05 path
-int launch_linear_bf16(const void* x, const void* W, long long M, int N, int K, const LinearEpilogue& epi, void* out,
-                       cudaStream_t st);
-int launch_row_logits_bf16(const void* qkv, int R, int C, int H, float* partial, int n_splits, cudaStream_t st);
-int launch_row_av_bf16(const void* probs, int ldp, const void* qkv, int R, int C, int H, void* ctx, cudaStream_t st);
-int row_logits_splits_bf16(int R, int C, int H);
+// umma_gemm.cu -- 16-bit (bf16 / fp16 operands, fp32 accumulate) tcgen05 path; fp16 != 0 selects fp16
+int launch_linear_16(const void* x, const void* W, long long M, int N, int K, int fp16, const LinearEpilogue& epi,
+                     void* out, cudaStream_t st);
+int launch_row_logits_16(const void* qkv, int R, int C, int H, int fp16, float* partial, int n_splits, cudaStream_t st);
+int launch_row_av_16(const void* probs, int ldp, const void* qkv, int R, int C, int H, int fp16, void* ctx,
+                     cudaStream_t st);
+int row_logits_splits_16(int R, int C, int H);
+int gemm_max_pairs();
 
 // col_attn_umma.cu
-int launch_col_attn_bf16(const void* qkv, int R, int C, int H, const uint8_t* pad, void* ctx, cudaStream_t st);
+int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, const uint8_t* pad, void* ctx, cudaStream_t st);
 
 }  // namespace rnamsm

@@ -1,8 +1,14 @@
-// bf16 tensor-core path: one persistent, warp-specialised tcgen05 GEMM serving the three dense
-// contractions of the forward.  Operands are staged in shared memory by TMA (SWIZZLE_128B),
-// multiplied by tcgen05.mma (cta_group::1, M=128, N=256, K=16 per instruction, fp32 accumulators
-// in TMEM, double-buffered so the epilogue of tile t overlaps the MMAs of tile t+1), and read
-// back with tcgen05.ld for the fused epilogues.
+// 16-bit tensor-core path: one persistent, warp-specialised tcgen05 GEMM serving the three dense
+// contractions of the forward, run by CTA PAIRS (cta_group::2): the two CTAs of a cluster sit on
+// the two SMs of one TPC and share one 256 x 256 accumulator tile -- each CTA stages its own
+// 128 rows of A and its own 128-row half of B, so per-SM operand traffic from L2 (the bound of a
+// single-CTA 128 x 256 kernel: 48 KiB per k-block) drops to 32 KiB and each MMA reads both halves
+// of B across the pair.  Operands come in through TMA (SWIZZLE_128B) into a 6-stage ring, are
+// multiplied by tcgen05.mma.cta_group::2 (M=256, N=256, K=16 per instruction, fp32 accumulators
+// in TMEM, double-buffered so the epilogue of tile t overlaps the MMAs of tile t+1) and leave
+// through tcgen05.ld -> registers -> swizzled smem staging -> TMA store (coalesced, clipped at
+// the tensor edge by the hardware).  The residual epilogue is a TMA reduce-add on the fp32
+// stream, so the epilogue never reads global memory.
 //
 //   DENSE : out[m,n] = epi( sum_k x[m,k] W[n,k] + b[n] )                 nn.Linear sites,
 //           modules.py:760-766 (q/k/v), :799 (out_proj), :424-426 (fc1/GELU/fc2), :314 (lm dense)
@@ -10,31 +16,43 @@
 //           (K-loop walks MSA rows; one 64-wide head slice per k-block, split-K over row ranges)
 //   AV    : ctx[r,i,h,:] = sum_j P[h,i,j] v[r,j,h,:]                            modules.py:797
 //           (P tile is the stationary A operand; B = V read in place as an MN-major operand,
-//            four MSA rows x 64 head dims per 256-wide N tile)
+//            four MSA rows x 64 head dims per 256-wide N tile, two rows per CTA of the pair)
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one
-// elected lane), warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4); warp 2 also owns the
-// TMEM allocation.  Pipelines: smem full/empty ring (kStages), TMEM full/empty (2 accumulators).
+// Operand element type is bf16 or fp16 (same tensor-core rate, kind::f16); fp16 carries three more
+// mantissa bits and is what the tied row-attention block uses (see api.cu).
+//
+// Warp roles (384 threads per CTA): warp 0 = TMA producer (one elected lane, both CTAs), warp 1 =
+// MMA issuer (one elected lane, leader CTA only), warp 2 = TMEM allocation, warp 3 idle,
+// warps 4..11 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4).
+// Pipelines: smem full/empty ring (full barriers live in the leader CTA and collect both CTAs'
+// TMA bytes; empty barriers are armed in both CTAs by a multicast tcgen05.commit), TMEM
+// full (multicast commit) / empty (leader barrier, remote arrivals from the peer's epilogue).
 #include "../../include/rnamsm_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "launch.h"
 
 namespace rnamsm {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 256;
-constexpr int BLOCK_K = 64;                      // one SWIZZLE_128B atom of bf16 along K
+constexpr int BLOCK_M = 128;                     // rows per CTA (256 per pair)
+constexpr int PAIR_M = 2 * BLOCK_M;
+constexpr int BLOCK_N = 256;                     // accumulator columns per pair (128 B rows staged per CTA)
+constexpr int HALF_N = BLOCK_N / 2;
+constexpr int BLOCK_K = 64;                      // one SWIZZLE_128B atom of 16-bit elements along K
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
-constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KiB
+constexpr int B_BYTES = HALF_N * BLOCK_K * 2;    // 16 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KiB per CTA per k-block
 constexpr int kTmemCols = 512;                   // 2 accumulator stages x 256 fp32 columns
-constexpr int kEpiWarps = 4;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kSmemBytes = kStages * STAGE_BYTES + 256 + 1024;  // tiles + barriers + align slack
+constexpr int kEpiWarps = 8;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+constexpr int EPI_BUF_BYTES = 32 * 128;          // one 32-row x 128 B staging box per epilogue warp
+constexpr int kSmemBytes = kStages * STAGE_BYTES + kEpiWarps * EPI_BUF_BYTES + 256 + 1024;
 
 enum { V_DENSE = 0, V_TIED = 1, V_AV = 2 };
 
@@ -45,16 +63,17 @@ struct GemmArgs {
   int R, C, H;
   int rows_per_split;
   int epi_kind;
+  int fp16;              // operand / 16-bit output element type: 0 = bf16, 1 = fp16
   const float* bias;
   float q_scale;
   int q_cols;
   const uint8_t* row_mask;
-  void* out;
+  void* out;             // TIED only (direct fp32 stores); the other variants store through tmap_out
   int ld_out;
 };
 
 struct TileCoord {
-  int m0, n0;            // element offsets of the tile inside the logical M / N extents
+  int m0, n0;            // element offsets of the PAIR tile inside the logical M / N extents
   int batch, split;
   int kb_begin, kb_count;
 };
@@ -64,17 +83,17 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile) {
   TileCoord t;
   if (kVariant == V_DENSE) {
     t.n0 = (tile % g.n_tiles) * BLOCK_N;
-    t.m0 = (tile / g.n_tiles) * BLOCK_M;
+    t.m0 = (tile / g.n_tiles) * PAIR_M;
     t.batch = 0; t.split = 0; t.kb_begin = 0; t.kb_count = g.k_blocks;
   } else if (kVariant == V_TIED) {
     t.n0 = (tile % g.n_tiles) * BLOCK_N;  tile /= g.n_tiles;
-    t.m0 = (tile % g.m_tiles) * BLOCK_M;  tile /= g.m_tiles;
+    t.m0 = (tile % g.m_tiles) * PAIR_M;   tile /= g.m_tiles;
     t.split = tile % g.splits;
     t.batch = tile / g.splits;
     t.kb_begin = t.split * g.rows_per_split;
     t.kb_count = min(g.R, t.kb_begin + g.rows_per_split) - t.kb_begin;
   } else {
-    t.m0 = (tile % g.m_tiles) * BLOCK_M;  tile /= g.m_tiles;
+    t.m0 = (tile % g.m_tiles) * PAIR_M;   tile /= g.m_tiles;
     t.n0 = (tile % g.n_tiles) * 4;        // first MSA row of the 4-row group
     t.batch = tile / g.n_tiles;
     t.split = 0; t.kb_begin = 0; t.kb_count = g.k_blocks;
@@ -82,88 +101,53 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile) {
   return t;
 }
 
-// ---- epilogues: 32 consecutive accumulator columns of one row per call ---------------------------
-template <int kVariant>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const TileCoord& t, int row_in_tile, int chunk,
-                                               const uint32_t (&acc)[32]) {
-  if (kVariant == V_DENSE) {
-    const long long m = (long long)t.m0 + row_in_tile;
-    const int n = t.n0 + chunk * 32;
-    if (m >= g.M || n >= g.N) return;
-    float v[32];
+// erf-GELU for the 16-bit epilogue: erfc(z) ~= (1 + a1 z + ... + a6 z^6)^-16 (Abramowitz & Stegun
+// 7.1.28, |error| <= 3e-7 -- far below the 16-bit output rounding), one MUFU.RCP + ~14 FMA-class
+// instructions per element instead of erff's ~30, which keeps the fc1 epilogue under the MMA time
+// of its tile.  The fp32 parity path keeps erff (simt_f32.cu).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float p = fmaf(z, 0.0000430638f, 0.0002765672f);
+  p = fmaf(p, z, 0.0001520143f);
+  p = fmaf(p, z, 0.0092705272f);
+  p = fmaf(p, z, 0.0422820123f);
+  p = fmaf(p, z, 0.0705230784f);
+  p = fmaf(p, z, 1.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  r *= r; r *= r; r *= r; r *= r;       // erfc(z)
+  const float h = 0.5f * x * r;
+  return x >= 0.f ? x - h : h;
+}
+
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
+  uint32_t r;
+  if (fp16)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// One 32-row x 128-byte box: lane `lane` writes its own row (8 x 16 B) into the SWIZZLE_128B
+// staging layout (16-byte chunk c of row r lives at chunk c ^ (r & 7)): conflict-free.
+__device__ __forceinline__ void stage_row(uint8_t* buf, int lane, const uint32_t (&w)[32]) {
+  uint8_t* row = buf + lane * 128;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(g.bias + n + i);
-      v[i] = __uint_as_float(acc[i]) + b.x;
-      v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
-      v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
-      v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
-    }
-    if (g.epi_kind == RNAMSM_EPI_BIAS_RESIDUAL) {
-      float* dst = reinterpret_cast<float*>(g.out) + (size_t)m * g.ld_out + n;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 r = *reinterpret_cast<float4*>(dst + i);
-        r.x += v[i]; r.y += v[i + 1]; r.z += v[i + 2]; r.w += v[i + 3];
-        *reinterpret_cast<float4*>(dst + i) = r;
-      }
-      return;
-    }
-    if (g.epi_kind == RNAMSM_EPI_BIAS_GELU) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-    } else if (n < g.q_cols) {  // q_cols is a multiple of 32: a chunk is entirely q or not
-      const float s = (g.row_mask && g.row_mask[m]) ? 0.f : g.q_scale;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= s;
-    }
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)m * g.ld_out + n;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      uint4 pk = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
-                            pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
-      *reinterpret_cast<uint4*>(dst + i) = pk;
-    }
-  } else if (kVariant == V_TIED) {
-    const int i = t.m0 + row_in_tile;
-    const int j0 = t.n0 + chunk * 32;
-    if (i >= g.C || j0 >= g.C) return;
-    float* dst = reinterpret_cast<float*>(g.out) + (((size_t)t.split * g.H + t.batch) * g.C + i) * g.C + j0;
-    if ((g.C & 3) == 0 && j0 + 32 <= g.C) {
-#pragma unroll
-      for (int k = 0; k < 32; k += 4)
-        *reinterpret_cast<float4*>(dst + k) = make_float4(__uint_as_float(acc[k]), __uint_as_float(acc[k + 1]),
-                                                          __uint_as_float(acc[k + 2]), __uint_as_float(acc[k + 3]));
-    } else {
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (j0 + k < g.C) dst[k] = __uint_as_float(acc[k]);
-    }
-  } else {
-    const int i = t.m0 + row_in_tile;
-    const int r = t.n0 + (chunk >> 1);
-    if (i >= g.C || r >= g.R) return;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + ((size_t)r * g.C + i) * g.ld_out + t.batch * 64 +
-                         (chunk & 1) * 32;
-#pragma unroll
-    for (int k = 0; k < 32; k += 8) {
-      uint4 pk = make_uint4(pack_bf16(__uint_as_float(acc[k]), __uint_as_float(acc[k + 1])),
-                            pack_bf16(__uint_as_float(acc[k + 2]), __uint_as_float(acc[k + 3])),
-                            pack_bf16(__uint_as_float(acc[k + 4]), __uint_as_float(acc[k + 5])),
-                            pack_bf16(__uint_as_float(acc[k + 6]), __uint_as_float(acc[k + 7])));
-      *reinterpret_cast<uint4*>(dst + k) = pk;
-    }
-  }
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
 
 template <int kVariant>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024 B alignment (descriptor base_offset = 0).
+  // SWIZZLE_128B tiles need 1024 B alignment (descriptor base_offset = 0).  The dynamic smem
+  // window starts at the same offset in both CTAs, so the carve-up below is identical in the pair.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+  uint8_t* epi_smem = smem + kStages * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * EPI_BUF_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -171,66 +155,71 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int total_tiles = g.m_tiles * g.n_tiles * g.batches * g.splits;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (kVariant != V_TIED) tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 2);                 // one arrive.expect_tx per CTA of the pair (leader's copy is used)
+      mbar_init(&empty_bar[s], 1);                // multicast tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&tmem_full[a], 1);                // multicast tcgen05.commit
+      mbar_init(&tmem_empty[a], 2 * kEpiWarps);   // epilogue warps of both CTAs (leader's copy is used)
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, kTmemCols);
-    tmem_relinquish();
+    tmem_alloc2(tmem_ptr, kTmemCols);
+    tmem_relinquish2();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
+    // ================================ TMA producer (both CTAs) =====================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const TileCoord t = decode_tile<kVariant>(g, tile);
         for (int kb = 0; kb < t.kb_count; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's full barrier
+          mbar_expect_tx_cluster(bar, STAGE_BYTES);
           if (kVariant == V_DENSE) {
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m0, 0);
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, t.n0, 0);
+            tma_load_3d_2sm(sa, &tmap_a, bar, kb * BLOCK_K, t.m0 + cta_rank * BLOCK_M, 0);
+            tma_load_3d_2sm(sb, &tmap_b, bar, kb * BLOCK_K, t.n0 + cta_rank * HALF_N, 0);
           } else if (kVariant == V_TIED) {
             const int r = t.kb_begin + kb;
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], t.batch * 64, t.m0, r);
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], (g.H + t.batch) * 64, t.n0, r);
+            tma_load_3d_2sm(sa, &tmap_a, bar, t.batch * 64, t.m0 + cta_rank * BLOCK_M, r);
+            tma_load_3d_2sm(sb, &tmap_b, bar, (g.H + t.batch) * 64, t.n0 + cta_rank * HALF_N, r);
           } else {
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m0, t.batch);
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], (2 * g.H + t.batch) * 64, kb * BLOCK_K, t.n0);
+            tma_load_3d_2sm(sa, &tmap_a, bar, kb * BLOCK_K, t.m0 + cta_rank * BLOCK_M, t.batch);
+            tma_load_3d_2sm(sb, &tmap_b, bar, (2 * g.H + t.batch) * 64, kb * BLOCK_K, t.n0 + cta_rank * 2);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, kVariant == V_AV ? 1 : 0);
+    // ================================ MMA issuer (leader CTA) =====================
+    if (leader && elect_one()) {
+      const uint32_t idesc = make_idesc_16(PAIR_M, BLOCK_N, g.fp16, 0, kVariant == V_AV ? 1 : 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const TileCoord t = decode_tile<kVariant>(g, tile);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -245,49 +234,157 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // A: K-major, 128 B rows, 8-row groups 1024 B apart; +32 B per 16-element k step.
             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
             uint64_t bdesc;
-            if (kVariant == V_AV)  // B: MN-major [4 r][64 j][64 d]: 64-wide N chunks 8 KiB apart,
+            if (kVariant == V_AV)  // B: MN-major [2 r][64 j][64 d]: 64-wide N chunks 8 KiB apart,
               bdesc = make_smem_desc_sw128(b_addr + k * (UMMA_K * 128), 64 * 128, 1024);  // 8-row k groups 1 KiB
             else
               bdesc = make_smem_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+            umma_16_2sm(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          umma_commit_2sm(&empty_bar[stage]);  // both CTAs' smem slots reusable once these MMAs have read them
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+        umma_commit_2sm(&tmem_full[acc]);      // accumulator complete -> epilogue warps of both CTAs
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
-    // ================================ epilogue ====================================
-    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
+  } else if (warp >= kFirstEpiWarp) {
+    // ================================ epilogue (both CTAs) ========================
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - kFirstEpiWarp) >> 2;    // accumulator columns [128*half, 128*half+128)
+    uint8_t* buf = epi_smem + (warp - kFirstEpiWarp) * EPI_BUF_BYTES;
+    const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
       const TileCoord t = decode_tile<kVariant>(g, tile);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
-      const int row_in_tile = quad * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + half * HALF_N + ((uint32_t)(quad * 32) << 16);
+      const int row0 = t.m0 + cta_rank * BLOCK_M + quad * 32;   // first logical row of this warp's box
+      auto release_acc = [&]() {                     // every tcgen05.ld of this tile has completed
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(empty_remote + acc * 8);
+      };
+
+      if (kVariant == V_TIED) {
+        // fp32 partial logits, direct stores (C need not be a multiple of 4)
+        const int i = row0 + lane;
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + chunk * 32, v);
-        tmem_ld_wait();
-        epilogue_chunk<kVariant>(g, t, row_in_tile, chunk, v);
+        for (int c = 0; c < HALF_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == HALF_N / 32 - 1) release_acc();
+          const int j0 = t.n0 + half * HALF_N + c * 32;
+          if (i >= g.C || j0 >= g.C) continue;
+          float* dst = reinterpret_cast<float*>(g.out) + (((size_t)t.split * g.H + t.batch) * g.C + i) * g.C + j0;
+          if ((g.C & 3) == 0 && j0 + 32 <= g.C) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              *reinterpret_cast<float4*>(dst + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]),
+                                                                __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (j0 + k < g.C) dst[k] = __uint_as_float(v[k]);
+          }
+        }
+      } else if (kVariant == V_DENSE && g.epi_kind == RNAMSM_EPI_BIAS_RESIDUAL) {
+        // out(fp32) += acc + bias: 32-column boxes, TMA reduce-add into the residual stream
+#pragma unroll 1
+        for (int c = 0; c < HALF_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == HALF_N / 32 - 1) release_acc();
+          const int n = t.n0 + half * HALF_N + c * 32;
+          if (n >= g.N || row0 >= g.M) continue;
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(g.bias + n + k);
+            v[k] = __float_as_uint(__uint_as_float(v[k]) + b.x);
+            v[k + 1] = __float_as_uint(__uint_as_float(v[k + 1]) + b.y);
+            v[k + 2] = __float_as_uint(__uint_as_float(v[k + 2]) + b.z);
+            v[k + 3] = __float_as_uint(__uint_as_float(v[k + 3]) + b.w);
+          }
+          if (lane == 0) bulk_wait_read0();            // the previous box has left the staging buffer
+          __syncwarp();
+          stage_row(buf, lane, v);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_3d(&tmap_out, buf, n, row0, 0);
+            bulk_commit();
+          }
+        }
+      } else {
+        // 16-bit outputs: 64-column boxes (128 B rows), TMA store
+#pragma unroll 1
+        for (int c = 0; c < HALF_N / 64; ++c) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(taddr + c * 64, v0);
+          tmem_ld_32x32(taddr + c * 64 + 32, v1);
+          tmem_ld_wait();
+          if (c == HALF_N / 64 - 1) release_acc();
+          uint32_t w[32];
+          int c0, c1, c2;
+          if (kVariant == V_DENSE) {
+            const int n = t.n0 + half * HALF_N + c * 64;
+            if (n >= g.N || row0 >= g.M) continue;
+            float s = 1.f;
+            if (g.epi_kind == RNAMSM_EPI_BIAS && n < g.q_cols) {   // q_cols is a multiple of 64
+              const int m = row0 + lane;
+              s = (g.row_mask && m < g.M && g.row_mask[m]) ? 0.f : g.q_scale;
+            }
+            const bool gelu = g.epi_kind == RNAMSM_EPI_BIAS_GELU;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n + k);
+              const float4 b1 = *reinterpret_cast<const float4*>(g.bias + n + 32 + k);
+              float a[8] = {__uint_as_float(v0[k]) + b0.x, __uint_as_float(v0[k + 1]) + b0.y,
+                            __uint_as_float(v0[k + 2]) + b0.z, __uint_as_float(v0[k + 3]) + b0.w,
+                            __uint_as_float(v1[k]) + b1.x, __uint_as_float(v1[k + 1]) + b1.y,
+                            __uint_as_float(v1[k + 2]) + b1.z, __uint_as_float(v1[k + 3]) + b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = gelu ? gelu_fast(a[e]) : a[e] * s;
+              w[k / 2] = pack16(a[0], a[1], g.fp16);
+              w[k / 2 + 1] = pack16(a[2], a[3], g.fp16);
+              w[16 + k / 2] = pack16(a[4], a[5], g.fp16);
+              w[16 + k / 2 + 1] = pack16(a[6], a[7], g.fp16);
+            }
+            c0 = n; c1 = row0; c2 = 0;
+          } else {  // V_AV: columns = (MSA row r, 64 head dims); rows = query column i
+            const int r = t.n0 + half * 2 + c;
+            if (r >= g.R || row0 >= g.C) continue;
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+              w[k / 2] = pack16(__uint_as_float(v0[k]), __uint_as_float(v0[k + 1]), g.fp16);
+              w[16 + k / 2] = pack16(__uint_as_float(v1[k]), __uint_as_float(v1[k + 1]), g.fp16);
+            }
+            c0 = t.batch * 64; c1 = row0; c2 = r;
+          }
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          stage_row(buf, lane, w);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_out, buf, c0, c1, c2);
+            bulk_commit();
+          }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait_all0();   // our global writes are complete before the CTA retires
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  cluster_sync();   // the peer's smem / barriers stay valid until both CTAs are done
+  if (warp == 2) tmem_dealloc2(tmem_base, kTmemCols);
 }
 
 int num_sms() {
@@ -301,15 +398,42 @@ int num_sms() {
   return n;
 }
 
+// CTA pairs that can be co-resident: a persistent grid must not exceed it (a pair that only starts
+// once another has finished its whole share would double the kernel time).  Not every GPC has an
+// even number of usable SMs, so this can be below num_sms() / 2.
+int g_max_pairs = 0;
+
 template <int kVariant>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int prof_class, cudaStream_t st) {
-  RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBytes));
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g,
+                   int prof_class, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytes));
+    attr_set = true;
+  }
+  if (g_max_pairs == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_sms(), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, umma_gemm_kernel<kVariant>, &cfg);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+    const char* env = getenv("RNAMSM_GEMM_PAIRS");
+    if (env && atoi(env) > 0) n = atoi(env);
+    g_max_pairs = std::min(n, num_sms() / 2);
+  }
   const long long total = (long long)g.m_tiles * g.n_tiles * g.batches * g.splits;
   RNAMSM_REQUIRE(total > 0 && total < (1LL << 31), "umma_gemm: tile count %lld out of range", total);
-  const int grid = (int)std::min<long long>(total, num_sms());
+  const int pairs = (int)std::min<long long>(total, g_max_pairs);
   ProfScope prof(prof_class, st);
-  umma_gemm_kernel<kVariant><<<grid, kThreads, kSmemBytes, st>>>(ta, tb, g);
+  umma_gemm_kernel<kVariant><<<2 * pairs, kThreads, kSmemBytes, st>>>(ta, tb, to, g);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -318,91 +442,129 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-int launch_linear_bf16(const void* x, const void* W, long long M, int N, int K, const LinearEpilogue& epi, void* out,
-                       cudaStream_t st) {
-  RNAMSM_REQUIRE(M > 0 && M < (1LL << 31), "linear_bf16: M=%lld out of range", M);
-  RNAMSM_REQUIRE(N % 32 == 0 && K % BLOCK_K == 0 && K >= BLOCK_K, "linear_bf16: N=%d must be a multiple of 32, K=%d of 64", N, K);
-  RNAMSM_REQUIRE(epi.bias != nullptr, "linear_bf16: bias required");
-  RNAMSM_REQUIRE(epi.q_cols % 32 == 0, "linear_bf16: q_cols=%d must be a multiple of 32", epi.q_cols);
-  CUtensorMap ta, tb;
+int launch_linear_16(const void* x, const void* W, long long M, int N, int K, int fp16, const LinearEpilogue& epi,
+                     void* out, cudaStream_t st) {
+  RNAMSM_REQUIRE(M > 0 && M < (1LL << 31), "linear_16: M=%lld out of range", M);
+  RNAMSM_REQUIRE(N % 64 == 0 && K % BLOCK_K == 0 && K >= BLOCK_K, "linear_16: N=%d and K=%d must be multiples of 64", N, K);
+  RNAMSM_REQUIRE(epi.bias != nullptr, "linear_16: bias required");
+  RNAMSM_REQUIRE(epi.q_cols % 64 == 0, "linear_16: q_cols=%d must be a multiple of 64", epi.q_cols);
+  const int in_dt = fp16 ? TMAP_F16 : TMAP_BF16;
+  CUtensorMap ta, tb, to;
   {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1};
     uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)M * K * 2};
     uint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
-    if (encode_tmap_bf16(&ta, x, 3, dims, strides, box)) return 3;
+    if (encode_tmap(&ta, in_dt, x, 3, dims, strides, box)) return 3;
   }
   {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, 1};
     uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)N * K * 2};
-    uint32_t box[3] = {BLOCK_K, BLOCK_N, 1};
-    if (encode_tmap_bf16(&tb, W, 3, dims, strides, box)) return 3;
+    uint32_t box[3] = {BLOCK_K, HALF_N, 1};
+    if (encode_tmap(&tb, in_dt, W, 3, dims, strides, box)) return 3;
+  }
+  if (epi.kind == RNAMSM_EPI_BIAS_RESIDUAL) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, 1};
+    uint64_t strides[2] = {(uint64_t)N * 4, (uint64_t)M * N * 4};
+    uint32_t box[3] = {32, 32, 1};
+    if (encode_tmap(&to, TMAP_F32, out, 3, dims, strides, box)) return 3;
+  } else {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, 1};
+    uint64_t strides[2] = {(uint64_t)N * 2, (uint64_t)M * N * 2};
+    uint32_t box[3] = {64, 32, 1};
+    if (encode_tmap(&to, in_dt, out, 3, dims, strides, box)) return 3;
   }
   GemmArgs g{};
-  g.m_tiles = ceil_div(M, BLOCK_M);
+  g.m_tiles = ceil_div(M, PAIR_M);
   g.n_tiles = ceil_div(N, BLOCK_N);
   g.batches = 1; g.splits = 1;
   g.k_blocks = K / BLOCK_K;
   g.M = (int)M; g.N = N;
+  g.fp16 = fp16;
   g.epi_kind = epi.kind; g.bias = epi.bias; g.q_scale = epi.q_scale; g.q_cols = epi.q_cols; g.row_mask = epi.row_mask;
   g.out = out; g.ld_out = N;
-  return launch_variant<V_DENSE>(ta, tb, g, linear_class(epi.kind, N, K), st);
+  return launch_variant<V_DENSE>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
 }
 
-int row_logits_splits_bf16(int R, int C, int H) {
-  const long long tiles = (long long)H * ceil_div(C, BLOCK_M) * ceil_div(C, BLOCK_N);
-  int want = (int)std::max<long long>(1, num_sms() / std::max<long long>(1, tiles));
+int gemm_max_pairs() { return g_max_pairs; }
+
+int row_logits_splits_16(int R, int C, int H) {
+  const long long tiles = (long long)H * ceil_div(C, PAIR_M) * ceil_div(C, BLOCK_N);
+  const int pairs = g_max_pairs > 0 ? g_max_pairs : num_sms() / 2;
+  // smallest split count whose tile total fills the 74 CTA pairs in whole waves as evenly as possible
+  int want = (int)std::max<long long>(1, (pairs + tiles - 1) / tiles);
+  if (tiles > pairs) {
+    // more tiles than pairs: pick the split count in [1, 4] with the best wave efficiency
+    double best = 0.0;
+    want = 1;
+    for (int s = 1; s <= 4; ++s) {
+      const long long tt = tiles * s;
+      const double eff = (double)tt / ((double)((tt + pairs - 1) / pairs) * pairs);
+      if (eff > best + 0.03) { best = eff; want = s; }
+    }
+  }
   want = std::min(want, std::max(1, R / 8));  // keep >= 8 rows (k-blocks) per split
   want = std::max(1, std::min(want, R));
   const int rps = ceil_div(R, want);
   return ceil_div(R, rps);  // every split non-empty
 }
 
-int launch_row_logits_bf16(const void* qkv, int R, int C, int H, float* partial, int n_splits, cudaStream_t st) {
-  RNAMSM_REQUIRE(n_splits >= 1 && n_splits <= R, "row_logits_bf16: n_splits=%d out of range for R=%d", n_splits, R);
+int launch_row_logits_16(const void* qkv, int R, int C, int H, int fp16, float* partial, int n_splits, cudaStream_t st) {
+  RNAMSM_REQUIRE(n_splits >= 1 && n_splits <= R, "row_logits_16: n_splits=%d out of range for R=%d", n_splits, R);
   const int rps = ceil_div(R, n_splits);
-  RNAMSM_REQUIRE((n_splits - 1) * rps < R, "row_logits_bf16: n_splits=%d leaves an empty split for R=%d", n_splits, R);
+  RNAMSM_REQUIRE((n_splits - 1) * rps < R, "row_logits_16: n_splits=%d leaves an empty split for R=%d", n_splits, R);
   const int ld = 3 * H * 64;
+  const int in_dt = fp16 ? TMAP_F16 : TMAP_BF16;
   CUtensorMap ta, tb;
   uint64_t dims[3] = {(uint64_t)ld, (uint64_t)C, (uint64_t)R};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)C * ld * 2};
   uint32_t box_a[3] = {BLOCK_K, BLOCK_M, 1};
-  uint32_t box_b[3] = {BLOCK_K, BLOCK_N, 1};
-  if (encode_tmap_bf16(&ta, qkv, 3, dims, strides, box_a)) return 3;
-  if (encode_tmap_bf16(&tb, qkv, 3, dims, strides, box_b)) return 3;
+  uint32_t box_b[3] = {BLOCK_K, HALF_N, 1};
+  if (encode_tmap(&ta, in_dt, qkv, 3, dims, strides, box_a)) return 3;
+  if (encode_tmap(&tb, in_dt, qkv, 3, dims, strides, box_b)) return 3;
   GemmArgs g{};
-  g.m_tiles = ceil_div(C, BLOCK_M);
+  g.m_tiles = ceil_div(C, PAIR_M);
   g.n_tiles = ceil_div(C, BLOCK_N);
   g.batches = H; g.splits = n_splits;
   g.rows_per_split = rps;
   g.R = R; g.C = C; g.H = H; g.M = C; g.N = C;
+  g.fp16 = fp16;
   g.out = partial;
-  return launch_variant<V_TIED>(ta, tb, g, KC_ROW_LOGITS, st);
+  return launch_variant<V_TIED>(ta, tb, ta, g, KC_ROW_LOGITS, st);
 }
 
-int launch_row_av_bf16(const void* probs, int ldp, const void* qkv, int R, int C, int H, void* ctx, cudaStream_t st) {
-  RNAMSM_REQUIRE(ldp % 8 == 0 && ldp >= C, "row_av_bf16: ldp=%d must be a multiple of 8 and >= C=%d", ldp, C);
+int launch_row_av_16(const void* probs, int ldp, const void* qkv, int R, int C, int H, int fp16, void* ctx,
+                     cudaStream_t st) {
+  RNAMSM_REQUIRE(ldp % 8 == 0 && ldp >= C, "row_av_16: ldp=%d must be a multiple of 8 and >= C=%d", ldp, C);
   const int ld = 3 * H * 64;
-  CUtensorMap ta, tb;
+  const int in_dt = fp16 ? TMAP_F16 : TMAP_BF16;
+  CUtensorMap ta, tb, to;
   {
     uint64_t dims[3] = {(uint64_t)C, (uint64_t)C, (uint64_t)H};
     uint64_t strides[2] = {(uint64_t)ldp * 2, (uint64_t)C * ldp * 2};
     uint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
-    if (encode_tmap_bf16(&ta, probs, 3, dims, strides, box)) return 3;
+    if (encode_tmap(&ta, in_dt, probs, 3, dims, strides, box)) return 3;
   }
   {
     uint64_t dims[3] = {(uint64_t)ld, (uint64_t)C, (uint64_t)R};
     uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)C * ld * 2};
-    uint32_t box[3] = {64, BLOCK_K, 4};
-    if (encode_tmap_bf16(&tb, qkv, 3, dims, strides, box)) return 3;
+    uint32_t box[3] = {64, BLOCK_K, 2};
+    if (encode_tmap(&tb, in_dt, qkv, 3, dims, strides, box)) return 3;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)(H * 64), (uint64_t)C, (uint64_t)R};
+    uint64_t strides[2] = {(uint64_t)H * 64 * 2, (uint64_t)C * H * 64 * 2};
+    uint32_t box[3] = {64, 32, 1};
+    if (encode_tmap(&to, in_dt, ctx, 3, dims, strides, box)) return 3;
   }
   GemmArgs g{};
-  g.m_tiles = ceil_div(C, BLOCK_M);
+  g.m_tiles = ceil_div(C, PAIR_M);
   g.n_tiles = ceil_div(R, 4);
   g.batches = H; g.splits = 1;
   g.k_blocks = ceil_div(C, BLOCK_K);
   g.R = R; g.C = C; g.H = H; g.M = C; g.N = R;
+  g.fp16 = fp16;
   g.out = ctx; g.ld_out = H * 64;
-  return launch_variant<V_AV>(ta, tb, g, KC_ROW_AV, st);
+  return launch_variant<V_AV>(ta, tb, to, g, KC_ROW_AV, st);
 }
 
 }  // namespace rnamsm

@@ -114,7 +114,7 @@ class MSATransformer(nn.Module, _PrecisionMixin):
 
     # -- C-ABI plumbing ------------------------------------------------------------------------
     def c_weights(self, code: int) -> L.ModelWeights:
-        key = (code,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (code, self._row_code) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._wstruct is not None and self._wstruct[0] == key:
             return self._wstruct[1]
         keep = []

@@ -38,7 +38,8 @@ def _pad_u8(self_attn_padding_mask: Optional[torch.Tensor], b: int) -> Optional[
 
 
 class _PrecisionMixin:
-    """``precision`` = 'bf16' (tcgen05 tensor cores, fp32 accumulate/residual) or 'fp32' (FFMA)."""
+    """``precision`` = 'bf16' (tcgen05 tensor cores, fp32 accumulate/residual; the tied row-attention
+    block runs with fp16 operands), 'bf16_pure' (bf16 everywhere), 'fp16', or 'fp32' (FFMA parity path)."""
 
     precision: str = _DEFAULT_PRECISION
 
@@ -52,6 +53,10 @@ class _PrecisionMixin:
     @property
     def _code(self) -> int:
         return L.dtype_code(self.precision)
+
+    @property
+    def _row_code(self) -> int:
+        return L.row_dtype_code(self.precision)
 
 
 def _linear(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, code: int, epilogue: int = L.EPI_BIAS,
@@ -123,29 +128,31 @@ class RowSelfAttention(_AxialAttentionBase):
         self._check_input(x, self_attn_mask)
         R, Cc, B, D = x.shape
         H = self.num_heads
-        code = self._code
+        code = self._row_code
         dt = L.torch_dtype(code)
         w_qkv, b_qkv, w_out, b_out = self._pack(code)
         out = torch.empty((R, Cc, B, D), dtype=torch.float32, device=x.device)
         probs = torch.empty((H, B, Cc, Cc), dtype=torch.float32, device=x.device)
         scaling = self.align_scaling(x)
+        # 16-bit path: q carries 64^-1/2 (exact), the 1/sqrt(R) goes on the fp32 logit sums (K5)
+        q_scale, logit_scale = (self.scaling, scaling / self.scaling) if code != L.F32 else (scaling, 1.0)
         with torch.cuda.device(x.device):
             st = L.stream_ptr()
             for b in range(B):
                 xb = x[:, :, b, :].to(dt).contiguous().view(R * Cc, D)
                 pad = _pad_u8(self_attn_padding_mask, b)
-                qkv = _linear(xb, w_qkv, b_qkv, code, L.EPI_BIAS, scaling, D, pad)
+                qkv = _linear(xb, w_qkv, b_qkv, code, L.EPI_BIAS, q_scale, D, pad)
                 splits = L.lib.rnamsm_row_attn_splits(R, Cc, H, code)
                 partial = torch.empty((splits, H, Cc, Cc), dtype=torch.float32, device=x.device)
                 L.check(L.lib.rnamsm_row_attn_logits(L.ptr(qkv), R, Cc, H, code, L.ptr(partial), splits, st), "row_attn_logits")
                 pmap = torch.empty((H, Cc, Cc), dtype=torch.float32, device=x.device)
-                if code == L.BF16:
+                if code != L.F32:
                     ldp = (Cc + 7) // 8 * 8
                     plp = torch.empty((H, Cc, ldp), dtype=dt, device=x.device)
                 else:
                     ldp, plp = Cc, None
-                L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), splits, H, Cc, L.ptr(pad), L.ptr(pmap), L.ptr(plp),
-                                                 ldp, code, st), "row_softmax")
+                L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), splits, H, Cc, L.ptr(pad), float(logit_scale),
+                                                 L.ptr(pmap), L.ptr(plp), ldp, code, st), "row_softmax")
                 ctx = torch.empty((R * Cc, D), dtype=dt, device=x.device)
                 L.check(L.lib.rnamsm_row_attn_av(L.ptr(plp if plp is not None else pmap), ldp, L.ptr(qkv), R, Cc, H,
                                                  code, L.ptr(ctx), st), "row_attn_av")
@@ -292,7 +299,7 @@ class AxialTransformerLayer(nn.Module, _PrecisionMixin):
     def c_weights(self, code: int) -> L.LayerWeights:
         """The rnamsm_layer_weights struct for this layer (device pointers into the packed
         weights; the struct keeps the tensors alive through ``_wstruct``)."""
-        key = (code,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (code, self._row_code) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._wstruct is not None and self._wstruct[0] == key:
             return self._wstruct[1]
         keep = []
@@ -302,16 +309,17 @@ class AxialTransformerLayer(nn.Module, _PrecisionMixin):
             keep.append(t)
             return t.data_ptr()
 
-        def attn(block: NormalizedResidualBlock) -> L.AttnWeights:
-            w_qkv, b_qkv, w_out, b_out = block.layer._pack(code)
+        def attn(block: NormalizedResidualBlock, blk_code: int) -> L.AttnWeights:
+            w_qkv, b_qkv, w_out, b_out = block.layer._pack(blk_code)
             keep.extend([w_qkv, b_qkv, w_out, b_out])
             return L.AttnWeights(f32(block.layer_norm.weight), f32(block.layer_norm.bias), w_qkv.data_ptr(),
-                                 b_qkv.data_ptr(), w_out.data_ptr(), b_out.data_ptr())
+                                 b_qkv.data_ptr(), w_out.data_ptr(), b_out.data_ptr(), blk_code)
 
         ffn = self.feed_forward_layer
         w1, b1, w2, b2 = ffn.layer._pack(code)
         keep.extend([w1, b1, w2, b2])
-        s = L.LayerWeights(attn(self.row_self_attention), attn(self.column_self_attention), f32(ffn.layer_norm.weight),
+        s = L.LayerWeights(attn(self.row_self_attention, self._row_code), attn(self.column_self_attention, code),
+                           f32(ffn.layer_norm.weight),
                            f32(ffn.layer_norm.bias), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr())
         self._wstruct = (key, s, keep)
         return s
@@ -335,7 +343,9 @@ class AxialTransformerLayer(nn.Module, _PrecisionMixin):
             nbytes = L.lib.rnamsm_workspace_bytes(R, Cc, D, H, F, code)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             for b in range(B):
-                xb = x[:, :, b, :].float().contiguous()  # fresh fp32 copy, updated in place by the kernels
+                # fresh fp32 copy (never a view of the caller's x): the kernels update it in place
+                xb = torch.empty((R, Cc, D), dtype=torch.float32, device=x.device)
+                xb.copy_(x[:, :, b, :])
                 pad = _pad_u8(self_attn_padding_mask, b)
                 pm = torch.empty((H, Cc, Cc), dtype=torch.float32, device=x.device) if need_head_weights else None
                 L.check(L.lib.rnamsm_layer_forward(C.byref(w), D, H, F, eps, L.ptr(xb), R, Cc, L.ptr(pad), code,

@@ -31,15 +31,16 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(raw, s), f"{s} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert _lib.lib.rnamsm_version() == 1
+    assert _lib.lib.rnamsm_version() == 2
     assert _lib.lib.rnamsm_launch_count() == 0
 
 
 def test_ctypes_struct_layout_matches_header():
     from rnamsm_b200 import _lib
     p = C.sizeof(C.c_void_p)
-    assert C.sizeof(_lib.AttnWeights) == 6 * p
-    assert C.sizeof(_lib.LayerWeights) == 2 * 6 * p + 6 * p
+    assert C.sizeof(_lib.AttnWeights) == 7 * p                # 6 pointers + int dtype (padded)
+    assert _lib.AttnWeights.dtype.offset == 6 * p
+    assert C.sizeof(_lib.LayerWeights) == 2 * 7 * p + 6 * p
     assert C.sizeof(_lib.ModelWeights) == 8 * 4 + 13 * p      # 7 ints + float, then 13 pointers
     assert _lib.ModelWeights.tok_emb.offset == 32
 
@@ -63,5 +64,5 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "UTMAREDG", "LDTM"):
         assert mnemonic in sass, mnemonic

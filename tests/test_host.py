@@ -83,7 +83,9 @@ def test_no_cpu_fallback(pkg):
     with pytest.raises(ValueError):
         pkg.RowSelfAttention(768, 8)          # head_dim must be 64
     with pytest.raises(ValueError):
-        model.set_precision("fp16")
+        model.set_precision("int8")
+    assert model.set_precision("fp16").precision == "fp16"
+    model.set_precision("bf16")
 
 
 def test_extract_features_format(pkg):
