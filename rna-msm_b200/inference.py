@@ -35,7 +35,7 @@ def extract_features(results: Dict[str, object], vocab: Vocab, num_layers: int) 
     return emb, atp
 
 
-def build_model(model_path: Optional[str], device: str = "cuda", precision: str = "bf16", embed_dim: int = 768,
+def build_model(model_path: Optional[str], device: str = "cuda", precision: str = "fp16", embed_dim: int = 768,
                 num_attention_heads: int = 12, num_layers: int = 10, embed_positions_msa: bool = True,
                 max_tokens: int = 16384, max_seqlen: int = 1024, seed: int = 42) -> Tuple[MSATransformer, Vocab]:
     alphabet = Alphabet.from_architecture("rna language")
@@ -85,7 +85,7 @@ def main(argv=None):
     ap.add_argument("--num_attention_heads", type=int, default=12)
     ap.add_argument("--num_layers", type=int, default=10)
     ap.add_argument("--no_embed_positions_msa", action="store_true")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "bf16_pure", "fp32"])
     a = ap.parse_args(argv)
     model, vocab = build_model(a.model_path, a.device, a.precision, a.embed_dim, a.num_attention_heads, a.num_layers,
                                not a.no_embed_positions_msa, a.max_tokens, a.max_seqlen)

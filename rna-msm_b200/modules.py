@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib as L
 
-_DEFAULT_PRECISION = os.environ.get("RNAMSM_PRECISION", "bf16")
+_DEFAULT_PRECISION = os.environ.get("RNAMSM_PRECISION", "fp16")
 
 
 def _infer_only(module: nn.Module) -> None:
@@ -38,8 +38,9 @@ def _pad_u8(self_attn_padding_mask: Optional[torch.Tensor], b: int) -> Optional[
 
 
 class _PrecisionMixin:
-    """``precision`` = 'bf16' (tcgen05 tensor cores, fp32 accumulate/residual; the tied row-attention
-    block runs with fp16 operands), 'bf16_pure' (bf16 everywhere), 'fp16', or 'fp32' (FFMA parity path)."""
+    """``precision``: 'fp16' (default: fp16 operands on the tcgen05 tensor cores, fp32 accumulate /
+    residual stream / LayerNorm / softmax), 'bf16' (bf16 operands except the tied row-attention
+    block, which stays fp16), 'bf16_pure' (bf16 everywhere) or 'fp32' (FFMA parity path)."""
 
     precision: str = _DEFAULT_PRECISION
 
