@@ -81,9 +81,12 @@ int rnamsm_embed_layernorm(const int64_t* tokens, int R, int C, const float* tok
                            uint8_t* pad_out, void* stream);
 
 /* K2 / K9 -- LayerNorm over the last dim (nn.LayerNorm(D), biased variance), fp32 in,
- * fp32 or bf16 out (modules.py:382,387; model.py:331-332,396). */
+ * fp32 / bf16 / fp16 out (modules.py:382,387; model.py:331-332,396).  tr_R, tr_C > 0 (with
+ * tr_R * tr_C == n_rows) additionally permutes the tokens from token-major (r * C + c) to
+ * column-major (c * R + r) order on the way out -- the layout the column-attention block works in;
+ * 0, 0 keeps the order. */
 int rnamsm_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows,
-                     int D, float eps, void* stream);
+                     int D, float eps, int tr_R, int tr_C, void* stream);
 
 /* K3 / K6-out / K8 -- nn.Linear with fused epilogue: out = epi(x[M,K] W[N,K]^T + bias[N]).
  * x, W in `dtype`.  For RNAMSM_EPI_BIAS: columns [0,q_cols) are multiplied by q_scale after the
@@ -118,8 +121,14 @@ int rnamsm_row_attn_av(const void* probs, int ldp, const void* qkv, int R, int C
 /* K7 -- column attention over the MSA depth, flash-style (modules.py:896-923): for every column c
  * and head h, ctx[i,c,h,:] = softmax_j(q[i,c,h,:].k[j,c,h,:]) v[j,c,h,:]; q already scaled by
  * 64^-0.5; keys with pad[j*C+c] != 0 get logit -10000 (modules.py:911-915).  R >= 2 (the R == 1
- * shortcut of modules.py:882-894 is handled by the caller as out_proj(v_proj(x))). */
-int rnamsm_col_attn(const void* qkv, int R, int C, int H, int dtype, const uint8_t* pad, void* ctx, void* stream);
+ * shortcut of modules.py:882-894 is handled by the caller as out_proj(v_proj(x))).
+ * qkv_col_major = 0: q|k|v is token-major [R, C, 3D] like every other activation;
+ * qkv_col_major = 1 (16-bit path only): q|k|v is [C, R, 3D], i.e. produced from a LayerNorm output
+ * written with tr_R / tr_C -- the rows a (column, head) problem reads are then 3D elements apart
+ * instead of C * 3D, which is what lets the TMA unit stream K/V.  pad and ctx are
+ * token-major ([R*C] and [R*C, D]) in both cases. */
+int rnamsm_col_attn(const void* qkv, int R, int C, int H, int dtype, int qkv_col_major, const uint8_t* pad, void* ctx,
+                    void* stream);
 
 /* K9b -- tied LM-head projection logits[m, v] = h[m,:] . E[v,:] + bias[v] (modules.py:318), fp32. */
 int rnamsm_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,

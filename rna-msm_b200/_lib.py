@@ -51,13 +51,13 @@ SIGNATURES = {
     "rnamsm_profile_class_name": (C.c_char_p, [_i]),
     "rnamsm_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_ll), _i]),
     "rnamsm_embed_layernorm": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
-    "rnamsm_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _f, _vp]),
+    "rnamsm_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _f, _i, _i, _vp]),
     "rnamsm_linear": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "rnamsm_row_attn_logits": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "rnamsm_row_attn_splits": (_i, [_i, _i, _i, _i]),
     "rnamsm_row_softmax": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _i, _i, _vp]),
     "rnamsm_row_attn_av": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
-    "rnamsm_col_attn": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rnamsm_col_attn": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnamsm_vocab_proj": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
     "rnamsm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "rnamsm_layer_forward": (_i, [C.POINTER(LayerWeights), _i, _i, _i, _f, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -203,7 +203,12 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   }
 
   // ---- column attention over the MSA depth                           modules.py:875-945
-  if ((rc = launch_layernorm(x, w->col.ln_w, w->col.ln_b, xn, col_dt, T, D, eps, st))) return rc;
+  // 16-bit path: LayerNorm writes its output in column-major token order (c * R + r), so the QKV GEMM
+  // produces q|k|v as [C, R, 3D] and the flash kernel's K/V boxes read rows 3D elements apart instead of
+  // C * 3D (one TMA row per 2 MiB page otherwise).  ctx comes back token-major for the out-projection.
+  const int col_major = is16(col_dt) && R > 1 ? 1 : 0;
+  if ((rc = launch_layernorm(x, w->col.ln_w, w->col.ln_b, xn, col_dt, T, D, eps, st, col_major ? R : 0, col_major ? C : 0)))
+    return rc;
   if (R == 1) {
     // single-row shortcut: out_proj(v_proj(x)), modules.py:882-894.  Project with the v rows only.
     LinearEpilogue ev{RNAMSM_EPI_BIAS, w->col.b_qkv + 2 * D, 1.f, 0, nullptr};
@@ -213,7 +218,7 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
     LinearEpilogue e{RNAMSM_EPI_BIAS, w->col.b_qkv, 1.0f / sqrtf(64.f), D, nullptr};  // q *= scaling, :905
     if ((rc = linear_any(xn, w->col.w_qkv, T, 3 * D, D, col_dt, e, qkv, st))) return rc;
     if (is16(col_dt)) {
-      if ((rc = launch_col_attn_16(qkv, R, C, H, col_dt == RNAMSM_F16, pad, ctx, st))) return rc;
+      if ((rc = launch_col_attn_16(qkv, R, C, H, col_dt == RNAMSM_F16, col_major, pad, ctx, st))) return rc;
     } else {
       if ((rc = launch_col_attn_f32((const float*)qkv, R, C, H, pad, (float*)ctx, st))) return rc;
     }
@@ -289,8 +294,8 @@ int rnamsm_embed_layernorm(const int64_t* tokens, int R, int C, const float* tok
 }
 
 int rnamsm_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
-                     float eps, void* stream) {
-  return launch_layernorm(x, w, b, y, y_dtype, n_rows, D, eps, (cudaStream_t)stream);
+                     float eps, int tr_R, int tr_C, void* stream) {
+  return launch_layernorm(x, w, b, y, y_dtype, n_rows, D, eps, (cudaStream_t)stream, tr_R, tr_C);
 }
 
 int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, int N, int K, int dtype, int epilogue,
@@ -319,9 +324,12 @@ int rnamsm_row_attn_av(const void* probs, int ldp, const void* qkv, int R, int C
   return launch_row_av_f32((const float*)probs, ldp, (const float*)qkv, R, C, H, (float*)ctx, (cudaStream_t)stream);
 }
 
-int rnamsm_col_attn(const void* qkv, int R, int C, int H, int dtype, const uint8_t* pad, void* ctx, void* stream) {
+int rnamsm_col_attn(const void* qkv, int R, int C, int H, int dtype, int qkv_col_major, const uint8_t* pad, void* ctx,
+                    void* stream) {
   RNAMSM_REQUIRE(R >= 2, "rnamsm_col_attn: R=%d (the R == 1 shortcut is out_proj(v_proj(x)))", R);
-  if (is16(dtype)) return launch_col_attn_16(qkv, R, C, H, dtype == RNAMSM_F16, pad, ctx, (cudaStream_t)stream);
+  RNAMSM_REQUIRE(!qkv_col_major || is16(dtype), "rnamsm_col_attn: the column-major q|k|v layout exists in the 16-bit path only");
+  if (is16(dtype))
+    return launch_col_attn_16(qkv, R, C, H, dtype == RNAMSM_F16, qkv_col_major, pad, ctx, (cudaStream_t)stream);
   return launch_col_attn_f32((const float*)qkv, R, C, H, pad, (float*)ctx, (cudaStream_t)stream);
 }
 

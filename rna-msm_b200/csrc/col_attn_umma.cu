@@ -15,6 +15,8 @@
 // math.  64 KiB smem and 128 TMEM columns per CTA -> 3 CTAs per SM interleave MMA and softmax.
 #include "../../include/rnamsm_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "launch.h"
 
 namespace rnamsm {
@@ -36,7 +38,7 @@ __device__ __forceinline__ float ex2(float x) {
 
 __global__ void __launch_bounds__(128)
 col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int R, int C,
-                     int H, int fp16, const uint8_t* __restrict__ pad, uint16_t* __restrict__ ctx) {
+                     int H, int fp16, int col_major, const uint8_t* __restrict__ pad, uint16_t* __restrict__ ctx) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
@@ -82,8 +84,9 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   auto load_kv = [&](int jb) {
     const int b = jb & 1;
     mbar_expect_tx(&kv_full[b], 2 * KV_BYTES);
-    tma_load_3d(sK + b * KV_BYTES, &tm_kv, &kv_full[b], D + h * HD, c, jb * BKV);
-    tma_load_3d(sV + b * KV_BYTES, &tm_kv, &kv_full[b], 2 * D + h * HD, c, jb * BKV);
+    tma_load_3d(sK + b * KV_BYTES, &tm_kv, &kv_full[b], D + h * HD, col_major ? jb * BKV : c, col_major ? c : jb * BKV);
+    tma_load_3d(sV + b * KV_BYTES, &tm_kv, &kv_full[b], 2 * D + h * HD, col_major ? jb * BKV : c,
+                col_major ? c : jb * BKV);
   };
   auto issue_s = [&](int jb) {  // S = Q K_jb^T
     const int b = jb & 1;
@@ -106,7 +109,7 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   if (leader) {
     mbar_expect_tx(q_full, Q_BYTES);
-    tma_load_3d(sQ, &tm_q, q_full, h * HD, c, i0);
+    tma_load_3d(sQ, &tm_q, q_full, h * HD, col_major ? i0 : c, col_major ? c : i0);
     load_kv(0);
     if (nblk > 1) load_kv(1);
     mbar_wait(q_full, 0);
@@ -225,14 +228,35 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 }  // namespace
 
-int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, const uint8_t* pad, void* ctx, cudaStream_t st) {
+int launch_col_attn_ws_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,
+                          cudaStream_t st);   // col_attn_ws.cu
+
+// Dispatch: MSAs deeper than one 128-row query tile run the persistent warp-specialised kernel
+// (col_attn_ws.cu: two query tiles ping-pong per CTA); shallow ones (R <= 128) keep this
+// one-tile-per-CTA kernel, whose single tile wastes nothing.  RNAMSM_COL_ATTN=small|ws forces one.
+int launch_col_attn_small_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,
+                             cudaStream_t st);
+int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,
+                       cudaStream_t st) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("RNAMSM_COL_ATTN");
+    forced = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'w' ? 2 : 0));
+  }
+  const bool use_ws = forced == 2 || (forced == 0 && R > 128);
+  return use_ws ? launch_col_attn_ws_16(qkv, R, C, H, fp16, col_major, pad, ctx, st)
+                : launch_col_attn_small_16(qkv, R, C, H, fp16, col_major, pad, ctx, st);
+}
+
+int launch_col_attn_small_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,
+                             cudaStream_t st) {
   RNAMSM_REQUIRE(R >= 1 && C >= 1 && H >= 1 && C <= 2147483647 / 1 && H <= 65535, "col_attn_bf16: bad shape");
   const int ld = 3 * H * HD;
   CUtensorMap tq, tkv;
-  uint64_t dims[3] = {(uint64_t)ld, (uint64_t)C, (uint64_t)R};
-  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)C * ld * 2};
-  uint32_t box_q[3] = {HD, 1, BQ};
-  uint32_t box_kv[3] = {HD, 1, BKV};
+  uint64_t dims[3] = {(uint64_t)ld, (uint64_t)(col_major ? R : C), (uint64_t)(col_major ? C : R)};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)(col_major ? R : C) * ld * 2};
+  uint32_t box_q[3] = {HD, (uint32_t)(col_major ? BQ : 1), (uint32_t)(col_major ? 1 : BQ)};
+  uint32_t box_kv[3] = {HD, (uint32_t)(col_major ? BKV : 1), (uint32_t)(col_major ? 1 : BKV)};
   const int in_dt = fp16 ? TMAP_F16 : TMAP_BF16;
   if (encode_tmap(&tq, in_dt, qkv, 3, dims, strides, box_q)) return 3;
   if (encode_tmap(&tkv, in_dt, qkv, 3, dims, strides, box_kv)) return 3;
@@ -240,7 +264,8 @@ int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, const uin
   dim3 grid(C, H, ceil_div(R, BQ));
   RNAMSM_REQUIRE(grid.z <= 65535, "col_attn_bf16: R too large");
   ProfScope prof(KC_COL_ATTN, st);
-  col_attn_umma_kernel<<<grid, 128, kSmem, st>>>(tq, tkv, R, C, H, fp16, pad, reinterpret_cast<uint16_t*>(ctx));
+  col_attn_umma_kernel<<<grid, 128, kSmem, st>>>(tq, tkv, R, C, H, fp16, col_major, pad,
+                                                 reinterpret_cast<uint16_t*>(ctx));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

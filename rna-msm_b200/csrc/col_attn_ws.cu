@@ -1,0 +1,403 @@
+// K7, 16-bit path, production kernel: warp-specialised flash-style column attention on tcgen05
+// (modules.py:896-923).  For every alignment column c and head h the MSA depth R is the sequence
+// axis:   ctx[i,c,h,:] = sum_j softmax_j(q[i,c,h,:] . k[j,c,h,:]) v[j,c,h,:]     (q pre-scaled by 64^-1/2)
+// The R x R probabilities are never materialised (the reference keeps [H,C,B,R,R] per layer).
+//
+// Persistent CTAs (one per SM).  A work item is (column c, head h, block of NT x 128 queries): NT
+// independent 128-row query tiles that share one K/V stream.  Each tile is its own pipeline
+// (its own MMA-issuing thread, softmax warpgroup, S / O accumulators in TMEM and P buffer); a step
+// of one tile is a serial chain  S ready -> tcgen05.ld -> max -> 64 x ex2 -> P to smem -> proxy
+// fence -> PV MMA  of ~2000 cycles that no amount of warps per tile shortens (measured: 1 or 2
+// threads per row, 1 or 2 issuing threads -> same time), so throughput = tiles in flight / chain
+// latency.  NT = 4 fills TMEM (4 x (64 S + 64 O) = 512 columns) and keeps the XU (MUFU.EX2, 16/clk/SM
+// measured -- the real bound of this kernel: 64 ex2 per 8192 tensor flops) busy; NT = 2 serves
+// shallow MSAs (R <= 256).  Items are numbered with the query block innermost, so the CTAs working
+// at the same moment share K/V through L2.
+//
+//   warp 0            TMA producer: Q tiles of the item and a K/V ring, 3-D boxes (64 d x 1 column
+//                     x rows) straight out of the packed q|k|v activation
+//   warps 1..3 (+0)   MMA issuers, one thread per tile: S_t = Q_t K_j^T (M128 N64 K64, fp32
+//                     in TMEM) issued ONE STEP AHEAD of the softmax, O_t (+)= P_t V_j accumulating in
+//                     TMEM; warp 1 also owns the TMEM allocation
+//   warps 4..4+4NT-1  softmax, one warpgroup per tile (thread = query row = TMEM lane):
+//                     S -> registers, running max with LAZY rescaling (O and l are only rescaled when
+//                     the row max grows by more than 2^8, FlashAttention-4 style: the stale reference
+//                     max cancels in O / l), p = ex2(s * log2e - m), P -> smem as the 16-bit K-major
+//                     SWIZZLE_128B A operand of the PV MMA.  O never leaves TMEM until the item ends.
+#include <stdlib.h>
+
+#include "../../include/rnamsm_b200.h"
+#include "common.cuh"
+#include "launch.h"
+
+namespace rnamsm {
+
+namespace {
+
+constexpr int BQ = 128, BKV = 64, HD = 64;
+constexpr int Q_BYTES = BQ * HD * 2;        // 16 KiB per tile
+constexpr int KV_BYTES = BKV * HD * 2;      // 8 KiB each for K and V
+constexpr int P_BYTES = BQ * BKV * 2;       // 16 KiB per tile
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;   // log2 units: P stays <= 2^8, exact in fp16 / bf16 range
+
+template <int NT>
+struct Cfg {
+  static constexpr int kQBufs = NT == 2 ? 2 : 1;        // Q double-buffered across items when smem allows
+  static constexpr int kKvStages = NT == 2 ? 4 : 3;
+  static constexpr int OFF_Q = 0;                        // [kQBufs][NT tiles]
+  static constexpr int OFF_KV = OFF_Q + kQBufs * NT * Q_BYTES;   // [stages][K | V]
+  static constexpr int OFF_P = OFF_KV + kKvStages * 2 * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + NT * P_BYTES;
+  static constexpr int kSmem = OFF_BAR + 512 + 1024;
+  static constexpr int kWarps = 4 + 4 * NT;              // 4 role warps + one softmax warpgroup per tile
+  static constexpr int kThreads = 32 * kWarps;           // NT = 4: 640 threads -> 96 registers each
+  static constexpr int kTmemCols = NT * 128;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct Item { int c, h, i0; };
+
+template <int NT>
+__device__ __forceinline__ Item decode_item(int item, int nqb, int H) {
+  Item it;
+  it.i0 = (item % nqb) * (NT * BQ);
+  item /= nqb;
+  it.h = item % H;
+  it.c = item / H;
+  return it;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(Cfg<NT>::kThreads, 1)
+col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int R, int C,
+                   int H, int fp16, int col_major, int n_items, const uint8_t* __restrict__ pad,
+                   uint16_t* __restrict__ ctx) {
+  using K = Cfg<NT>;
+  constexpr int kKvStages = K::kKvStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
+  uint64_t* q_full = bars;                      // [2]
+  uint64_t* q_empty = bars + 2;                 // [2]
+  uint64_t* kv_full = bars + 4;                 // [4]
+  uint64_t* kv_empty = bars + 8;                // [4]
+  uint64_t* s_full = bars + 12;                 // [4] per tile
+  uint64_t* s_free = bars + 16;
+  uint64_t* p_full = bars + 20;
+  uint64_t* pv_done = bars + 24;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int D = H * HD;
+  const int nblk = (R + BKV - 1) / BKV;
+  const int nqb = (R + NT * BQ - 1) / (NT * BQ);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], NT);               // one commit per MMA issuer
+    }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(&kv_full[b], 1);
+      mbar_init(&kv_empty[b], NT);              // one commit per MMA issuer
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_free[b], 4);
+      mbar_init(&p_full[b], 4);
+      mbar_init(&pv_done[b], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, K::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // Single-thread roles: TMA producer = warp 0 lane 0; MMA issuer of tile t = lane 0 of warp 1 + t for
+  // t < 3 and lane 1 of warp 0 for t = 3 (two roles on divergent lanes of warp 0: independent thread
+  // scheduling interleaves them, and it keeps the CTA at 20 warps = 96 registers per thread).
+  const int mma_tile = (lane == 0 && warp >= 1 && warp <= 3 && warp - 1 < NT) ? warp - 1
+                       : ((NT == 4 && warp == 0 && lane == 1) ? 3 : -1);
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    {
+      int kv_stage = 0;
+      uint32_t kv_phase = 0;
+      int li = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+        const Item it = decode_item<NT>(item, nqb, H);
+        const int qb = K::kQBufs == 2 ? (li & 1) : 0;
+        const int quse = K::kQBufs == 2 ? (li >> 1) : li;     // how many times this buffer was used before
+        mbar_wait_relaxed(&q_empty[qb], (quse & 1) ^ 1);
+        mbar_expect_tx(&q_full[qb], NT * Q_BYTES);
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          tma_load_3d(smem + K::OFF_Q + (qb * NT + t) * Q_BYTES, &tm_q, &q_full[qb], it.h * HD,
+                      col_major ? it.i0 + t * BQ : it.c, col_major ? it.c : it.i0 + t * BQ);
+        for (int j = 0; j < nblk; ++j) {
+          mbar_wait_relaxed(&kv_empty[kv_stage], kv_phase ^ 1);
+          uint8_t* sk = smem + K::OFF_KV + kv_stage * 2 * KV_BYTES;
+          mbar_expect_tx(&kv_full[kv_stage], 2 * KV_BYTES);
+          tma_load_3d(sk, &tm_kv, &kv_full[kv_stage], D + it.h * HD, col_major ? j * BKV : it.c,
+                      col_major ? it.c : j * BKV);
+          tma_load_3d(sk + KV_BYTES, &tm_kv, &kv_full[kv_stage], 2 * D + it.h * HD, col_major ? j * BKV : it.c,
+                      col_major ? it.c : j * BKV);
+          if (++kv_stage == kKvStages) { kv_stage = 0; kv_phase ^= 1; }
+        }
+      }
+    }
+  } else if (mma_tile >= 0) {
+    // ================================ MMA issuer of tile t =========================
+    {
+      const int t = mma_tile;
+      const uint32_t idesc_s = make_idesc_16(BQ, BKV, fp16, 0, 0);  // Q (K-major) x K (K-major)
+      const uint32_t idesc_o = make_idesc_16(BQ, HD, fp16, 0, 1);   // P (K-major) x V (MN-major)
+      const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const long long total_steps = (long long)my_items * nblk;
+      const uint32_t tmem_S = tmem_base + t * BKV, tmem_O = tmem_base + NT * BKV + t * HD;
+      const uint32_t pa = smem_u32(smem + K::OFF_P + t * P_BYTES);
+      // cursor of the S issue (runs one step ahead of the PV issue)
+      long long gs = 0;
+      int s_li = 0, s_j = 0, s_stage = 0;
+      uint32_t s_phase = 0;
+      auto issue_s = [&]() {
+        const int qb = K::kQBufs == 2 ? (s_li & 1) : 0;
+        const int quse = K::kQBufs == 2 ? (s_li >> 1) : s_li;
+        if (s_j == 0) mbar_wait_relaxed(&q_full[qb], quse & 1);
+        mbar_wait_relaxed(&kv_full[s_stage], s_phase);
+        if (gs > 0) mbar_wait_relaxed(&s_free[t], (uint32_t)((gs - 1) & 1));   // softmax t has S(gs-1) in registers
+        tc_fence_after();
+        const uint32_t ka = smem_u32(smem + K::OFF_KV + s_stage * 2 * KV_BYTES);
+        const uint32_t qa = smem_u32(smem + K::OFF_Q + (qb * NT + t) * Q_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_16(tmem_S, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024),
+                  idesc_s, (uint32_t)(k != 0));
+        umma_commit(&s_full[t]);
+        if (s_j == nblk - 1) umma_commit(&q_empty[qb]);            // this tile's Q fully consumed
+        ++gs;
+        if (++s_j == nblk) { s_j = 0; ++s_li; }
+        if (++s_stage == kKvStages) { s_stage = 0; s_phase ^= 1; }
+      };
+      int o_j = 0, o_stage = 0;
+      if (total_steps > 0) issue_s();
+      for (long long g = 0; g < total_steps; ++g) {
+        if (g + 1 < total_steps) issue_s();
+        const uint32_t va = smem_u32(smem + K::OFF_KV + o_stage * 2 * KV_BYTES + KV_BYTES);
+        mbar_wait_relaxed(&p_full[t], (uint32_t)(g & 1));                  // P_t(g) in smem, O_t rescaled if needed
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_16(tmem_O, make_smem_desc_sw128(pa + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 2048, 8192, 1024),
+                  idesc_o, (uint32_t)((o_j | k) != 0));
+        umma_commit(&pv_done[t]);
+        umma_commit(&kv_empty[o_stage]);                           // this tile is done with K_j and V_j
+        if (++o_j == nblk) o_j = 0;
+        if (++o_stage == kKvStages) o_stage = 0;
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + 4 * NT) {
+    // ================================ softmax warpgroups ==========================
+    const int t = (warp - 4) >> 2;                 // tile
+    const int quad = warp & 3;                     // TMEM lane quadrant of this warp
+    const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t tmem_S = tmem_base + t * BKV + lane_off;
+    const uint32_t tmem_O = tmem_base + NT * BKV + t * HD + lane_off;
+    uint8_t* prow = smem + K::OFF_P + t * P_BYTES + row * 128;
+    const float neg_masked = -10000.f;             // masked_fill value, modules.py:911-915
+    long long g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode_item<NT>(item, nqb, H);
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nblk; ++j, ++g) {
+        const int j0 = j * BKV;
+        mbar_wait(&s_full[t], (uint32_t)(g & 1));
+        tc_fence_after();
+        uint32_t sv[2][32];
+        tmem_ld_32x32(tmem_S, sv[0]);
+        tmem_ld_32x32(tmem_S + 32, sv[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);    // S buffer may be overwritten by the next step's S
+
+        if (pad != nullptr || j0 + BKV > R) {      // warp-uniform slow path: key masks
+          uint32_t mask_lo = 0, mask_hi = 0;
+          if (pad != nullptr) {
+            const int ja = j0 + lane, jb = j0 + 32 + lane;
+            mask_lo = __ballot_sync(0xffffffffu, ja < R && pad[(size_t)ja * C + it.c] != 0);
+            mask_hi = __ballot_sync(0xffffffffu, jb < R && pad[(size_t)jb * C + it.c] != 0);
+          }
+          const int n_valid = R - j0;
+#pragma unroll
+          for (int e = 0; e < BKV; ++e) {
+            const uint32_t mbits = (e < 32) ? mask_lo : mask_hi;
+            float v = __uint_as_float(sv[e >> 5][e & 31]);
+            if ((mbits >> (e & 31)) & 1u) v = neg_masked;
+            if (e >= n_valid) v = -INFINITY;       // key row does not exist
+            sv[e >> 5][e & 31] = __float_as_uint(v);
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[0][e]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[0][e + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[1][e]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[1][e + 1]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * kLog2e;   // log2 domain; finite (>= 1 real key)
+        // lazy rescale: keep the old reference unless the max grew by more than the threshold
+        float factor = 1.f;
+        const bool grow = mx > m_ref + kRescaleThreshold;   // true on the first block (m_ref = -inf)
+        if (grow) {
+          factor = ex2(m_ref - mx);                          // 0 on the first block
+          m_ref = mx;
+          l_run *= factor;
+        }
+        const bool rescale = (j > 0) && __any_sync(0xffffffffu, grow);
+        float ps0 = 0.f, ps1 = 0.f;
+        // exponentials in place, packed pairwise into the low half of sv as they are produced
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float a0 = ex2(fmaf(__uint_as_float(sv[hlf][e]), kLog2e, -m_ref));
+            const float a1 = ex2(fmaf(__uint_as_float(sv[hlf][e + 1]), kLog2e, -m_ref));
+            ps0 += a0;
+            ps1 += a1;
+            sv[hlf][e >> 1] = fp16 ? pack_f16(a0, a1) : pack_bf16(a0, a1);
+          }
+        }
+        l_run += ps0 + ps1;
+        if (g > 0) {                                // PV(g-1) done: P buffer free, O_t stable
+          mbar_wait(&pv_done[t], (uint32_t)((g - 1) & 1));
+          tc_fence_after();
+        }
+        if (rescale) {                              // warp-uniform; rare once the max has settled
+          uint32_t ov[32];
+#pragma unroll 1
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            tmem_ld_32x32(tmem_O + hlf * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) ov[d] = __float_as_uint(__uint_as_float(ov[d]) * factor);
+            tmem_st_32x32(tmem_O + hlf * 32, ov);
+          }
+          tmem_st_wait();
+        }
+        // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk ch of row r lives at chunk (ch ^ (r & 7)).
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t* w = &sv[ch >> 2][(ch & 3) * 4];
+          *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor-core (async) proxy
+        tc_fence_before();          // our tcgen05.ld / st precede the MMA that follows the barrier
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // ---- item epilogue: O / l -> ctx -----------------------------------------------------------
+      mbar_wait(&pv_done[t], (uint32_t)((g - 1) & 1));
+      tc_fence_after();
+      const int i = it.i0 + t * BQ + row;
+      const float inv = 1.f / l_run;
+      uint16_t* dst = ctx + ((size_t)i * C + it.c) * D + it.h * HD;
+#pragma unroll 1
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tmem_O + hlf * 32, ov);
+        tmem_ld_wait();
+        if (i < R) {
+#pragma unroll
+          for (int d = 0; d < 32; d += 8) {
+            uint4 val;
+            if (fp16)
+              val = make_uint4(pack_f16(__uint_as_float(ov[d]) * inv, __uint_as_float(ov[d + 1]) * inv),
+                               pack_f16(__uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv),
+                               pack_f16(__uint_as_float(ov[d + 4]) * inv, __uint_as_float(ov[d + 5]) * inv),
+                               pack_f16(__uint_as_float(ov[d + 6]) * inv, __uint_as_float(ov[d + 7]) * inv));
+            else
+              val = make_uint4(pack_bf16(__uint_as_float(ov[d]) * inv, __uint_as_float(ov[d + 1]) * inv),
+                               pack_bf16(__uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv),
+                               pack_bf16(__uint_as_float(ov[d + 4]) * inv, __uint_as_float(ov[d + 5]) * inv),
+                               pack_bf16(__uint_as_float(ov[d + 6]) * inv, __uint_as_float(ov[d + 7]) * inv));
+            *reinterpret_cast<uint4*>(dst + hlf * 32 + d) = val;
+          }
+        }
+      }
+      tc_fence_before();            // O loads precede the next item's first PV (ordered via p_full)
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, K::kTmemCols);
+}
+
+template <int NT>
+int launch_nt(const CUtensorMap& tq, const CUtensorMap& tkv, int R, int C, int H, int fp16, int col_major,
+              const uint8_t* pad, void* ctx, cudaStream_t st) {
+  using K = Cfg<NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_ws_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmem));
+    attr_set = true;
+  }
+  const long long n_items = (long long)C * H * ((R + NT * BQ - 1) / (NT * BQ));
+  RNAMSM_REQUIRE(n_items < (1LL << 31), "col_attn_ws: too many work items");
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int grid = (int)std::min<long long>(n_items, sms);
+  ProfScope prof(KC_COL_ATTN, st);
+  col_attn_ws_kernel<NT><<<grid, K::kThreads, K::kSmem, st>>>(tq, tkv, R, C, H, fp16, col_major, (int)n_items, pad,
+                                                            reinterpret_cast<uint16_t*>(ctx));
+  count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int launch_col_attn_ws_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,
+                          cudaStream_t st) {
+  RNAMSM_REQUIRE(R >= 1 && C >= 1 && H >= 1, "col_attn_ws: bad shape");
+  const int ld = 3 * H * HD;
+  CUtensorMap tq, tkv;
+  // token-major q|k|v [R, C, 3D]: the rows of one column are C*3D elements apart (every 128 B row of a
+  // box in a different 2 MiB page once the activation outgrows the TLB: measured ~27 cycles per row in
+  // the TMA unit, the bound of this kernel).  column-major [C, R, 3D]: rows 3D elements apart.
+  uint64_t dims[3] = {(uint64_t)ld, (uint64_t)(col_major ? R : C), (uint64_t)(col_major ? C : R)};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)(col_major ? R : C) * ld * 2};
+  uint32_t box_q[3] = {HD, (uint32_t)(col_major ? BQ : 1), (uint32_t)(col_major ? 1 : BQ)};
+  uint32_t box_kv[3] = {HD, (uint32_t)(col_major ? BKV : 1), (uint32_t)(col_major ? 1 : BKV)};
+  const int in_dt = fp16 ? TMAP_F16 : TMAP_BF16;
+  if (encode_tmap(&tq, in_dt, qkv, 3, dims, strides, box_q)) return 3;
+  if (encode_tmap(&tkv, in_dt, qkv, 3, dims, strides, box_kv)) return 3;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("RNAMSM_COL_NT");
+    forced = e ? atoi(e) : 0;
+  }
+  const int nt = forced == 2 || forced == 4 ? forced : (R > 2 * BQ ? 4 : 2);
+  return nt == 4 ? launch_nt<4>(tq, tkv, R, C, H, fp16, col_major, pad, ctx, st)
+                 : launch_nt<2>(tq, tkv, R, C, H, fp16, col_major, pad, ctx, st);
+}
+
+}  // namespace rnamsm

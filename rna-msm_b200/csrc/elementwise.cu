@@ -117,7 +117,7 @@ constexpr int kLnWarps = 8;
 template <int kOut>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_kernel(const float* x, const float* __restrict__ w, const float* __restrict__ b,
-                 void* y, long long n_rows, int D, float eps) {  // x may alias y (in-place final LN)
+                 void* y, long long n_rows, int D, float eps, int tr_R, int tr_C) {  // x may alias y (in-place final LN)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / 128;
   for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < n_rows;
@@ -128,8 +128,10 @@ layernorm_kernel(const float* x, const float* __restrict__ w, const float* __res
     for (int i = 0; i < kMaxVec; ++i)
       if (i < nv) v[i] = *reinterpret_cast<const float4*>(src + lane * 4 + i * 128);
     warp_layernorm(v, nv, D, eps, w, b, lane);
+    // optional token transpose: input row r * C + c -> output row c * R + r (column attention layout)
+    const long long orow = tr_C > 0 ? (row % tr_C) * tr_R + row / tr_C : row;
     if constexpr (kOut != 0) {
-      uint16_t* dst = reinterpret_cast<uint16_t*>(y) + (size_t)row * D;
+      uint16_t* dst = reinterpret_cast<uint16_t*>(y) + (size_t)orow * D;
 #pragma unroll
       for (int i = 0; i < kMaxVec; ++i)
         if (i < nv) {
@@ -138,7 +140,7 @@ layernorm_kernel(const float* x, const float* __restrict__ w, const float* __res
           *reinterpret_cast<uint2*>(dst + lane * 4 + i * 128) = pk;
         }
     } else {
-      float* dst = reinterpret_cast<float*>(y) + (size_t)row * D;
+      float* dst = reinterpret_cast<float*>(y) + (size_t)orow * D;
 #pragma unroll
       for (int i = 0; i < kMaxVec; ++i)
         if (i < nv) *reinterpret_cast<float4*>(dst + lane * 4 + i * 128) = v[i];
@@ -243,17 +245,19 @@ int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, i
 }
 
 int launch_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
-                     float eps, cudaStream_t st) {
+                     float eps, cudaStream_t st, int tr_R, int tr_C) {
+  RNAMSM_REQUIRE(tr_C <= 0 || (long long)tr_R * tr_C == n_rows, "layernorm: transpose shape %d x %d != %lld rows", tr_R, tr_C, n_rows);
+  RNAMSM_REQUIRE(tr_C <= 0 || (const void*)x != (const void*)y, "layernorm: the transposing form cannot run in place");
   RNAMSM_REQUIRE(D % 128 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d must be a multiple of 128 <= 1024", D);
   if (n_rows <= 0) return 0;
   const int blocks = (int)std::min<long long>((n_rows + kLnWarps - 1) / kLnWarps, 148LL * 32);
   ProfScope prof(KC_LAYERNORM, st);
   if (y_dtype == 1)
-    layernorm_kernel<1><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
+    layernorm_kernel<1><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
   else if (y_dtype == 2)
-    layernorm_kernel<2><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
+    layernorm_kernel<2><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
   else
-    layernorm_kernel<0><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps);
+    layernorm_kernel<0><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

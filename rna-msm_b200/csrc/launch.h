@@ -28,8 +28,9 @@ struct ProfScope {
 int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, int vocab, const float* pos_emb,
                     int n_pos, const float* row_pos, const float* ln_w, const float* ln_b, int D, int pad_idx,
                     float eps, float* x_out, uint8_t* pad_out, cudaStream_t st);
+// tr_R, tr_C > 0: write the output in column-major token order, y[c * tr_R + r] = LN(x[r * tr_C + c])
 int launch_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
-                     float eps, cudaStream_t st);
+                     float eps, cudaStream_t st, int tr_R = 0, int tr_C = 0);
 int launch_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float logit_scale,
                        float* probs_out, void* probs_lp, int ld_lp, int dtype, cudaStream_t st);
 int launch_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
@@ -68,6 +69,7 @@ int row_logits_splits_16(int R, int C, int H);
 int gemm_max_pairs();
 
 // col_attn_umma.cu
-int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, const uint8_t* pad, void* ctx, cudaStream_t st);
+int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,
+                       cudaStream_t st);
 
 }  // namespace rnamsm

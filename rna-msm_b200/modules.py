@@ -191,7 +191,7 @@ class ColumnSelfAttention(_AxialAttentionBase):
                     pad = _pad_u8(self_attn_padding_mask, b)
                     qkv = _linear(xb, w_qkv, b_qkv, code, L.EPI_BIAS, self.scaling, D, None)
                     ctx = torch.empty((R * Cc, D), dtype=dt, device=x.device)
-                    L.check(L.lib.rnamsm_col_attn(L.ptr(qkv), R, Cc, H, code, L.ptr(pad), L.ptr(ctx), st), "col_attn")
+                    L.check(L.lib.rnamsm_col_attn(L.ptr(qkv), R, Cc, H, code, 0, L.ptr(pad), L.ptr(ctx), st), "col_attn")
                     ob = _linear(ctx, w_out, b_out, code)
                 out[:, :, b, :] = ob.view(R, Cc, D).float()
         attn = torch.ones(H, Cc, B, 1, 1, device=x.device, dtype=x.dtype) if R == 1 else None
@@ -257,7 +257,7 @@ class NormalizedResidualBlock(nn.Module, _PrecisionMixin):
         with torch.cuda.device(x.device):
             L.check(L.lib.rnamsm_layernorm(L.ptr(xc), L.ptr(self.layer_norm.weight), L.ptr(self.layer_norm.bias),
                                            L.ptr(xn), L.F32, xc.numel() // xc.shape[-1], xc.shape[-1],
-                                           float(self.layer_norm.eps), L.stream_ptr()), "layernorm")
+                                           float(self.layer_norm.eps), 0, 0, L.stream_ptr()), "layernorm")
         outputs = self.layer(xn, *args, **kwargs)
         if isinstance(outputs, tuple):
             y, *out = outputs

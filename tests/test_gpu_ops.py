@@ -76,8 +76,15 @@ def test_layernorm(L, rows, code):
     ref = O.layer_norm(x.double(), w.double(), b.double())
     y = torch.empty(rows, D, dtype=L.torch_dtype(code), device="cuda")
     xd, wd, bd = x.cuda(), w.cuda(), b.cuda()      # named: a temporary would be freed before the launch
-    L.check(L.lib.rnamsm_layernorm(L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(y), code, rows, D, O.LN_EPS, L.stream_ptr()))
+    L.check(L.lib.rnamsm_layernorm(L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(y), code, rows, D, O.LN_EPS, 0, 0,
+                                   L.stream_ptr()))
     assert rel(y, ref) < (2e-6 if code == 0 else 5e-3 if code == 1 else 6e-4)
+    if rows == 1000:       # token transpose on the way out: row r*C + c -> row c*R + r
+        R_, C_ = 40, 25
+        yt = torch.empty(rows, D, dtype=L.torch_dtype(code), device="cuda")
+        L.check(L.lib.rnamsm_layernorm(L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(yt), code, rows, D, O.LN_EPS, R_, C_,
+                                       L.stream_ptr()))
+        assert torch.equal(yt.view(C_, R_, D), y.view(R_, C_, D).transpose(0, 1))
 
 
 # ------------------------------------------------------------------------------------------ K3/K6/K8
@@ -176,7 +183,8 @@ def test_row_attention_chain(L, R, C, code):
 
 # ------------------------------------------------------------------------------------------ K7
 @pytest.mark.parametrize("R,C,with_pad", [(2, 5, False), (9, 7, True), (64, 3, False), (65, 4, True), (130, 6, True),
-                                          (300, 2, False)])
+                                          (300, 2, False), (257, 3, True), (300, 7, True), (520, 13, False),
+                                          (1030, 2, True)])
 @pytest.mark.parametrize("code", [0, 1, 2], ids=["f32", "bf16", "f16"])
 def test_column_attention(L, R, C, with_pad, code):
     qkv, q64 = make_qkv(R, C, 31, code, L, 0.5)
@@ -194,8 +202,13 @@ def test_column_attention(L, R, C, with_pad, code):
     ctx_ref = torch.einsum("hcij,jchd->ichd", att.softmax(-1), v).reshape(R * C, D)
     ctx = torch.empty(R * C, D, dtype=L.torch_dtype(code), device="cuda")
     pad_u8 = pad.to(torch.uint8).cuda() if pad is not None else None
-    L.check(L.lib.rnamsm_col_attn(L.ptr(qkv), R, C, H, code, L.ptr(pad_u8), L.ptr(ctx), L.stream_ptr()))
+    L.check(L.lib.rnamsm_col_attn(L.ptr(qkv), R, C, H, code, 0, L.ptr(pad_u8), L.ptr(ctx), L.stream_ptr()))
     assert rel(ctx, ctx_ref) < tol(code)
+    if code != 0:          # same problem with q|k|v handed over column-major [C, R, 3D]; ctx stays token-major
+        qkv_t = qkv.transpose(0, 1).contiguous()
+        ctx2 = torch.empty_like(ctx)
+        L.check(L.lib.rnamsm_col_attn(L.ptr(qkv_t), R, C, H, code, 1, L.ptr(pad_u8), L.ptr(ctx2), L.stream_ptr()))
+        assert torch.equal(ctx2, ctx)
 
 
 # ------------------------------------------------------------------------------------------ K9b
@@ -210,6 +223,6 @@ def test_vocab_proj(L):
 def test_error_paths(L):
     x = torch.zeros(4, 100, device="cuda")
     with pytest.raises(RuntimeError, match="multiple of 128"):
-        L.check(L.lib.rnamsm_layernorm(L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), 0, 4, 100, 1e-5, L.stream_ptr()), "ln")
+        L.check(L.lib.rnamsm_layernorm(L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), 0, 4, 100, 1e-5, 0, 0, L.stream_ptr()), "ln")
     with pytest.raises(RuntimeError, match="R=1"):
-        L.check(L.lib.rnamsm_col_attn(L.ptr(x), 1, 4, 12, 0, None, L.ptr(x), L.stream_ptr()), "col")
+        L.check(L.lib.rnamsm_col_attn(L.ptr(x), 1, 4, 12, 0, 0, None, L.ptr(x), L.stream_ptr()), "col")

@@ -54,8 +54,10 @@ def main():
         ctx = torch.empty(M, D, device=dev, dtype=dt)
         ms = timeit(lambda: L.check(L.lib.rnamsm_row_attn_av(L.ptr(probs), ldp, L.ptr(qkv), R, C, H, code, L.ptr(ctx), st)))
         print(f"{name} row_av     R={R} C={C}: {ms:.3f} ms  {2.0 * R * C * C * D / ms / 1e9:.0f} TFLOP/s", flush=True)
-        ms = timeit(lambda: L.check(L.lib.rnamsm_col_attn(L.ptr(qkv), R, C, H, code, None, L.ptr(ctx), st)))
-        print(f"{name} col_attn   R={R} C={C}: {ms:.3f} ms  {4.0 * R * R * C * D / ms / 1e9:.0f} TFLOP/s", flush=True)
+        for cm in (0, 1):
+            ms = timeit(lambda: L.check(L.lib.rnamsm_col_attn(L.ptr(qkv), R, C, H, code, cm, None, L.ptr(ctx), st)))
+            print(f"{name} col_attn   R={R} C={C} col_major={cm}: {ms:.3f} ms  {4.0 * R * R * C * D / ms / 1e9:.0f} TFLOP/s",
+                  flush=True)
         if code == L.BF16:
             print("gemm pairs:", L.lib.rnamsm_gemm_pairs(), flush=True)
         break_after = os.environ.get("GEMM_BENCH_ONE")
