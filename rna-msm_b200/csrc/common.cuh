@@ -244,6 +244,20 @@ __device__ __forceinline__ void umma_16(uint32_t d_tmem, uint64_t adesc, uint64_
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M = 128 rows = lanes, 16-bit elements packed two per
+// 32-bit column) comes from tensor memory -- used for P V with P written by tcgen05.st.
+__device__ __forceinline__ void umma_16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ---- thread-block clusters / CTA pairs (cta_group::2) -----------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -383,6 +397,26 @@ __host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int fp16, int
   const uint32_t fmt = fp16 ? 0u : 1u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes of work) ------------
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // ---- misc math -----------------------------------------------------------------------------
