@@ -1,0 +1,260 @@
+"""One deep MSA across the GPUs of a box (BASELINE configs 4 and 5).
+
+What shards how (follows the reference's math, not BASELINE.json's wording):
+
+* tied row attention (modules.py:752-821) sums its logits over MSA rows -> shard ROWS: rank g owns
+  rows [g R/n, (g+1) R/n), computes the partial logits of its rows (scaled with the GLOBAL row
+  count, modules.py:713-715), one sum over ranks of the [H, C, C] fp32 logits per layer, softmax
+  replicated, AV + out-projection local.
+* column attention (modules.py:875-924) attends OVER rows (einsum "icnhd,jcnhd->hcnij", :907), so it
+  is not local to a row shard: it shards by COLUMNS.  Per layer the LayerNorm output of the column
+  block travels row-shard -> column-shard (all-to-all, 16-bit), the block's contribution
+  out_proj(attn(.)) travels back (all-to-all, 16-bit) and is added to the fp32 residual stream,
+  which never leaves its row shard.  K/V all-gather was rejected: (n-1) x more bytes.
+* embedding, LayerNorms, FFN, final LayerNorm: token-local, stay in the row shard.
+
+``ShardedMSAForward`` is the host-side schedule: shard plan, collectives, re-layouts.  What one
+rank computes between collectives is delegated to an ops object: ``CudaShardOps`` (the C-ABI
+kernels; the product) -- tests inject a CPU implementation to exercise this schedule under
+``gloo`` with world_size 2.  Collectives here are plain ``torch.distributed`` (NCCL over NVLink on
+the box); the fused peer-memory variants plug in at the two marked sites.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class ShardPlan:
+    """Row / column ranges of every rank for an R x C token grid over n ranks."""
+
+    def __init__(self, R: int, C: int, world: int, rank: int):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError(f"bad world/rank {world}/{rank}")
+        if R % world or C % world:
+            raise ValueError(
+                f"sharded forward needs depth R={R} and columns C={C} divisible by the number of ranks {world} "
+                "(pad the MSA with <pad> rows / columns; both are masked out of every attention)")
+        self.R, self.C, self.world, self.rank = R, C, world, rank
+        self.Rn, self.Cn = R // world, C // world
+        self.r0, self.c0 = rank * self.Rn, rank * self.Cn
+
+    def rows(self, rank: Optional[int] = None) -> slice:
+        g = self.rank if rank is None else rank
+        return slice(g * self.Rn, (g + 1) * self.Rn)
+
+    def cols(self, rank: Optional[int] = None) -> slice:
+        g = self.rank if rank is None else rank
+        return slice(g * self.Cn, (g + 1) * self.Cn)
+
+    def bytes_per_layer(self, D: int = 768, H: int = 12, act_bytes: int = 2, splits: int = 1) -> Dict[str, int]:
+        """NVLink bytes one rank SENDS per layer (what the scaling model in DESIGN.md uses)."""
+        n = self.world
+        a2a = self.Rn * self.C * D * act_bytes * (n - 1) // n
+        ar = 2 * (n - 1) * splits * H * self.C * self.C * 4 // n           # ring all-reduce volume per rank
+        return {"all_to_all_fwd": a2a, "all_to_all_back": a2a, "logit_all_reduce": ar}
+
+
+class ShardedMSAForward:
+    """MSATransformer.forward (model.py:338-416) for ONE MSA sharded over a process group.
+
+    Every rank passes the same full ``tokens [1, R, C]``.  Returns the reference's result dict with
+    ``row_attentions [1, N, H, C, C]`` complete on every rank and ``representations[N]`` holding this
+    rank's ROW SHARD ``[1, R/n, C, D]`` (rank 0 owns MSA row 0, the source of ``*_emb.npy``);
+    ``gather_rows=True`` all-gathers the full ``[1, R, C, D]``."""
+
+    def __init__(self, ops, num_layers: int, group=None):
+        self.ops = ops
+        self.num_layers = num_layers
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    # -- collectives (the two sites a fused peer-memory kernel replaces) --------------------------
+    def _sum_over_ranks(self, partial: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
+        return partial
+
+    def _exchange(self, send: torch.Tensor) -> torch.Tensor:
+        """send [n, ...] (chunk d goes to rank d) -> recv [n, ...] (chunk s came from rank s)."""
+        if self.world == 1:
+            return send
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv
+
+    @torch.no_grad()
+    def forward(self, tokens: torch.Tensor, need_head_weights: bool = True, gather_rows: bool = False,
+                pad_idx: int = 1) -> Dict[str, object]:
+        assert tokens.ndim == 3 and tokens.shape[0] == 1, "one MSA per call: tokens [1, R, C]"
+        _, R, C = tokens.shape
+        plan = ShardPlan(R, C, self.world, self.rank)
+        n, Rn, Cn = plan.world, plan.Rn, plan.Cn
+        ops, N = self.ops, self.num_layers
+        tok = tokens[0]
+        pad_full = tok.eq(pad_idx)
+        has_pad = bool(pad_full.any())
+        pad_rows = pad_full[plan.rows()].contiguous() if has_pad else None          # [Rn, C] this rank's rows
+        pad_cols = pad_full[:, plan.cols()].contiguous() if has_pad else None       # [R, Cn] this rank's columns
+        key_pad = pad_full[0].contiguous() if has_pad else None                     # MSA row 0, modules.py:780-784
+
+        x = ops.embed(tok[plan.rows()].contiguous(), plan.r0, R)                    # [Rn*C, D] fp32
+        D = x.shape[-1]
+        maps = ops.new_maps(N, C) if need_head_weights else None
+        for l in range(N):
+            # ---- tied row attention on the row shard ----------------------------------------------
+            partial = ops.row_logits(l, x, Rn, C, pad_rows, R)                      # [S, H, C, C] fp32, local rows
+            partial = self._sum_over_ranks(partial)                                 # <-- fused P2P site 1
+            ops.row_finish(l, x, partial, Rn, C, key_pad, R, None if maps is None else maps[l])
+            # ---- column attention on the column shard ---------------------------------------------
+            xn = ops.col_prepare(l, x, Rn, C)                                       # [Rn*C, D] 16-bit (fp32 path: fp32)
+            send = xn.view(Rn, n, Cn, D).permute(1, 0, 2, 3).contiguous()           # [n(dest), Rn, Cn, D]
+            recv = self._exchange(send)                                             # [n(src), Rn, Cn, D] == [R, Cn, D]
+            delta = ops.col_block(l, recv.view(R * Cn, D), R, Cn, pad_cols)         # [R*Cn, D] == [n(dest), Rn, Cn, D]
+            back = self._exchange(delta.view(n, Rn, Cn, D))                         # [n(src cols), Rn, Cn, D]  <-- site 2
+            ops.add_delta(x, back, Rn, n, Cn)                                       # x[r, (s, c), :] += back[s, r, c, :]
+            # ---- feed-forward on the row shard ----------------------------------------------------
+            ops.ffn(l, x, Rn * C)
+        ops.final_ln(x, Rn * C)
+        rep = x.view(1, Rn, C, D)
+        if gather_rows and n > 1:
+            full = [torch.empty_like(rep) for _ in range(n)]
+            dist.all_gather(full, rep.contiguous(), group=self.group)
+            rep = torch.cat(full, 1)
+        out: Dict[str, object] = {"logits": None, "representations": {N: rep}, "row_shard": (plan.r0, plan.r0 + Rn)}
+        if maps is not None:
+            out["row_attentions"] = maps.view(1, N, maps.shape[1], C, C)
+        return out
+
+
+class CudaShardOps:
+    """What one rank computes between collectives, through the C ABI (no fallback)."""
+
+    def __init__(self, model):
+        from . import _lib as L
+        from .modules import _linear
+        self.L, self._linear, self.m = L, _linear, model
+        self.code = model._code                  # column block / FFN operand type
+        self.row_code = model._row_code          # tied row block operand type
+        self.D, self.H = model.embed_dim, model.num_attention_heads
+        self.dev = model.device
+        self._qkv = None
+        self._splits = 1
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def _ln(self, x, ln: torch.nn.LayerNorm, code: int, T: int) -> torch.Tensor:
+        L = self.L
+        y = torch.empty((T, self.D), dtype=L.torch_dtype(code), device=x.device)
+        L.check(L.lib.rnamsm_layernorm(L.ptr(x), L.ptr(ln.weight), L.ptr(ln.bias), L.ptr(y), code, T, self.D,
+                                       float(ln.eps), 0, 0, L.stream_ptr()), "layernorm")
+        return y
+
+    @staticmethod
+    def _u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        return None if mask is None else mask.to(torch.uint8).contiguous()
+
+    # -- phases ---------------------------------------------------------------------------------------
+    def new_maps(self, N: int, C: int) -> torch.Tensor:
+        return torch.empty((N, self.H, C, C), dtype=torch.float32, device=self.dev)
+
+    def embed(self, tokens_rows: torch.Tensor, r0: int, R_global: int) -> torch.Tensor:
+        L, m = self.L, self.m
+        Rn, C = tokens_rows.shape
+        if m.msa_position_embedding is not None and R_global > 1024:
+            raise RuntimeError("Using model with MSA position embedding trained on maximum MSA depth of 1024, "
+                               f"but received {R_global} alignments.")
+        x = torch.empty((Rn * C, self.D), dtype=torch.float32, device=self.dev)
+        row_pos = None
+        if m.msa_position_embedding is not None:
+            row_pos = m.msa_position_embedding.detach().reshape(-1)[r0:r0 + Rn].float().contiguous()
+        self._keep = row_pos
+        toks = tokens_rows.long().contiguous()
+        L.check(L.lib.rnamsm_embed_layernorm(
+            L.ptr(toks), Rn, C, L.ptr(m.embed_tokens.weight), m.embed_tokens.weight.shape[0],
+            L.ptr(m.embed_positions.weight), m.embed_positions.weight.shape[0], L.ptr(row_pos),
+            L.ptr(m.emb_layer_norm_before.weight), L.ptr(m.emb_layer_norm_before.bias), self.D, m.vocab.pad_idx,
+            float(m.emb_layer_norm_before.eps), L.ptr(x), None, L.stream_ptr()), "embed_layernorm")
+        return x
+
+    def row_logits(self, l, x, Rn, C, pad_rows, R_global) -> torch.Tensor:
+        L, H, D, code = self.L, self.H, self.D, self.row_code
+        blk = self.m.layers[l].row_self_attention
+        w_qkv, b_qkv, _, _ = blk.layer._pack(code)
+        xn = self._ln(x, blk.layer_norm, code, Rn * C)
+        q_scale = 0.125 if code != L.F32 else 0.125 / math.sqrt(R_global)           # align_scaling uses the GLOBAL depth
+        self._pad_rows_u8 = self._u8(pad_rows)
+        self._qkv = self._linear(xn, w_qkv, b_qkv, code, L.EPI_BIAS, q_scale, D, self._pad_rows_u8)
+        self._splits = L.lib.rnamsm_row_attn_splits(Rn, C, H, code)
+        partial = torch.empty((self._splits, H, C, C), dtype=torch.float32, device=x.device)
+        L.check(L.lib.rnamsm_row_attn_logits(L.ptr(self._qkv), Rn, C, H, code, L.ptr(partial), self._splits,
+                                             L.stream_ptr()), "row_attn_logits")
+        return partial
+
+    def row_finish(self, l, x, partial, Rn, C, key_pad, R_global, map_out) -> None:
+        L, H, D, code = self.L, self.H, self.D, self.row_code
+        blk = self.m.layers[l].row_self_attention
+        _, _, w_out, b_out = blk.layer._pack(code)
+        pmap = map_out if map_out is not None else torch.empty((H, C, C), dtype=torch.float32, device=x.device)
+        logit_scale = 1.0 / math.sqrt(R_global) if code != L.F32 else 1.0
+        if code != L.F32:
+            ldp = (C + 7) // 8 * 8
+            plp = torch.empty((H, C, ldp), dtype=L.torch_dtype(code), device=x.device)
+        else:
+            ldp, plp = C, None
+        kp = self._u8(key_pad)
+        L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), partial.shape[0], H, C, L.ptr(kp), float(logit_scale),
+                                         L.ptr(pmap), L.ptr(plp), ldp, code, L.stream_ptr()), "row_softmax")
+        ctx = torch.empty((Rn * C, D), dtype=L.torch_dtype(code), device=x.device)
+        L.check(L.lib.rnamsm_row_attn_av(L.ptr(plp if plp is not None else pmap), ldp, L.ptr(self._qkv), Rn, C, H, code,
+                                         L.ptr(ctx), L.stream_ptr()), "row_attn_av")
+        self._linear(ctx, w_out, b_out, code, L.EPI_BIAS_RESIDUAL, out=x)
+        self._qkv = None
+
+    def col_prepare(self, l, x, Rn, C) -> torch.Tensor:
+        return self._ln(x, self.m.layers[l].column_self_attention.layer_norm, self.code, Rn * C)
+
+    def col_block(self, l, xn_cols, R, Cn, pad_cols) -> torch.Tensor:
+        L, H, D, code = self.L, self.H, self.D, self.code
+        blk = self.m.layers[l].column_self_attention
+        w_qkv, b_qkv, w_out, b_out = blk.layer._pack(code)
+        xn_cols = xn_cols.contiguous()
+        if R == 1:                                                                   # modules.py:882-894
+            v = self._linear(xn_cols, w_qkv[2 * D:], b_qkv[2 * D:], code)
+            return self._linear(v, w_out, b_out, code)
+        qkv = self._linear(xn_cols, w_qkv, b_qkv, code, L.EPI_BIAS, 0.125, D, None)
+        ctx = torch.empty((R * Cn, D), dtype=L.torch_dtype(code), device=xn_cols.device)
+        pu8 = self._u8(pad_cols)
+        L.check(L.lib.rnamsm_col_attn(L.ptr(qkv), R, Cn, H, code, 0, L.ptr(pu8), L.ptr(ctx), L.stream_ptr()), "col_attn")
+        return self._linear(ctx, w_out, b_out, code)                                 # bias only: the delta travels back
+
+    def add_delta(self, x, back, Rn, n, Cn) -> None:
+        x.view(Rn, n, Cn, self.D).add_(back.permute(1, 0, 2, 3))                     # fp32 += 16-bit, strided read
+
+    def ffn(self, l, x, T) -> None:
+        L, code = self.L, self.code
+        blk = self.m.layers[l].feed_forward_layer
+        w1, b1, w2, b2 = blk.layer._pack(code)
+        xn = self._ln(x, blk.layer_norm, code, T)
+        h = self._linear(xn, w1, b1, code, L.EPI_BIAS_GELU)
+        self._linear(h, w2, b2, code, L.EPI_BIAS_RESIDUAL, out=x)
+
+    def final_ln(self, x, T) -> None:
+        L, ln = self.L, self.m.emb_layer_norm_after
+        L.check(L.lib.rnamsm_layernorm(L.ptr(x), L.ptr(ln.weight), L.ptr(ln.bias), L.ptr(x), L.F32, T, self.D,
+                                       float(ln.eps), 0, 0, L.stream_ptr()), "layernorm")
+
+
+def sharded_forward(model, tokens: torch.Tensor, group=None, need_head_weights: bool = True,
+                    gather_rows: bool = False) -> Dict[str, object]:
+    """Convenience: run ``model`` (an eval-mode ``MSATransformer`` replicated on every rank's GPU) on one
+    MSA sharded over ``group``."""
+    L = __import__("rnamsm_b200")._lib
+    L.require_cuda(tokens, "tokens")
+    L.device_check(tokens.device)
+    with torch.cuda.device(tokens.device):
+        return ShardedMSAForward(CudaShardOps(model), model.num_layers, group).forward(
+            tokens, need_head_weights=need_head_weights, gather_rows=gather_rows, pad_idx=model.vocab.pad_idx)

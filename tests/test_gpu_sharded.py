@@ -1,0 +1,78 @@
+"""GPU: the sharded single-MSA forward (rna-msm_b200/sharded.py) through the C-ABI kernels.
+world 1 (always): the per-phase ops must reproduce MSATransformer.forward exactly (same kernels, same
+order).  world 2 (needs two GPUs; skipped otherwise): NCCL all-reduce of the tied logits + the two
+all-to-all re-layouts against the single-GPU forward of the same model."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import msa_ref as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(pkg, layers, precision, device):
+    vocab = pkg.Vocab(pkg.Alphabet())
+    m = pkg.MSATransformer(vocab, num_layers=layers, precision=precision)
+    m.load_state_dict(O.make_weights(9, num_layers=layers, sharpen=2.0), strict=True)
+    return m.eval().to(device)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("pads", [(0, 0), (3, 2)], ids=["nopad", "pad"])
+def test_world1_matches_model_forward(precision, pads):
+    import rnamsm_b200 as pkg
+    from rnamsm_b200.sharded import sharded_forward
+    m = _model(pkg, 3, precision, "cuda")
+    tokens = O.make_tokens(40, 70, 4, pad_cols=pads[0], pad_rows=pads[1]).cuda()
+    ref = m(tokens, repr_layers=[3], need_head_weights=True, want_logits=False)
+    out = sharded_forward(m, tokens)
+    tol = 2e-6 if precision == "fp32" else 2e-3      # 16-bit: delta rounded once more to 16 bits on its way back
+    assert O.rel_err(out["representations"][3].cpu(), ref["representations"][3].cpu()) < tol
+    assert O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"].cpu()) < tol
+
+
+def _worker(rank, world, port, precision, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import rnamsm_b200 as pkg
+        from rnamsm_b200.sharded import sharded_forward
+        m = _model(pkg, 3, precision, f"cuda:{rank}")
+        tokens = O.make_tokens(64, 96, 4, pad_cols=2, pad_rows=2).to(f"cuda:{rank}")
+        ref = m(tokens, repr_layers=[3], need_head_weights=True, want_logits=False)
+        out = sharded_forward(m, tokens, gather_rows=True)
+        torch.cuda.synchronize()
+        q.put((rank, O.rel_err(out["representations"][3].cpu(), ref["representations"][3].cpu()),
+               O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"].cpu())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_world2_nccl_matches_single_gpu(precision):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29710 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, precision, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    tol = 2e-5 if precision == "fp32" else 3e-3
+    for rank, e_rep, e_att in results:
+        assert e_rep < tol and e_att < tol, (rank, e_rep, e_att)
