@@ -126,8 +126,8 @@ def cpu_reference_sample(R, C, embed_positions_msa, threads=None):
     shape + the embedding, fp32, all host threads.  Returns (seconds for the sample, threads)."""
     import torch
     from oracle import msa_ref as O
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core (count reported in the JSON)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     sd = O.make_weights(42, num_layers=1, embed_positions_msa=embed_positions_msa)
     tokens = O.make_tokens(R, C, 0)
     with torch.no_grad():
@@ -210,7 +210,7 @@ def run_ours(args):
 
     def step_device():
         if shard:
-            return sharded_forward(model, tok_dev)
+            return sharded_forward(model, tok_dev, fused=args.fused)
         return model(tok_dev, repr_layers=[NL], need_head_weights=True, want_logits=False)
 
     emb_host = torch.empty((C - 1, D), dtype=torch.float32).pin_memory()
@@ -219,7 +219,7 @@ def run_ours(args):
     def step_e2e():
         t = tok_host.cuda(non_blocking=True)
         if shard:
-            out = sharded_forward(model, t)
+            out = sharded_forward(model, t, fused=args.fused)
             if rank == 0:                                           # rank 0 owns MSA row 0 and writes the files
                 att = out["row_attentions"][..., 1:, 1:].reshape(-1, C - 1, C - 1)
                 atp_host.copy_(att, non_blocking=True)
@@ -277,6 +277,8 @@ def run_ours(args):
         e2e_value = jobs * tokens_per_step / (e2e_s / args.steps)
         peaks = measured_peaks()
         fl = flops_breakdown(R, C)
+        if shard:                                       # per-rank share of the one sharded MSA
+            fl = {k: v / world for k, v in fl.items()}
         gemm_classes = ["linear_qkv", "linear_out_resid", "linear_fc1_gelu", "linear_fc2_resid"]
         gemm_ms = sum(prof[k][0] for k in gemm_classes)
         gemm_launches = sum(prof[k][1] for k in gemm_classes)
@@ -298,10 +300,10 @@ def run_ours(args):
             "share_of_kernel_time": round(gemm_ms / kernel_ms_total, 4) if kernel_ms_total else None,
             "traffic": None,
             "class_time_share": shares, "class_tflops": tflops,
-            "whole_forward_tflops": round(O.flops(R, C) * args.steps / (ms_total * 1e-3) / 1e12, 2),
+            "whole_forward_tflops_per_gpu": round(O.flops(R, C) / (world if shard else 1) * args.steps / (ms_total * 1e-3) / 1e12, 2),
         }
         cpu = None
-        if world == 1 or True:
+        if world == 1:                                  # contract: the CPU baseline is timed at N=1 only
             t_emb, t_layer, threads = cpu_reference_sample(R, C, epm)
             per_fwd = t_emb + NL * t_layer
             cpu = {"value": tokens_per_step / per_fwd, "unit": "tokens/s", "cores": threads, "kind": "port",
@@ -318,7 +320,8 @@ def run_ours(args):
                                     "stream / LayerNorm / softmax / exported maps" if args.precision != "fp32"
                                     else "fp32 FFMA parity path",
                        "parallelism": (f"one MSA sharded over {world} GPUs: rows (tied row attention, fp32 logit all-reduce) "
-                                       f"<-> columns (column attention, 16-bit all-to-all), NCCL over NVLink") if shard
+                                       f"<-> columns (column attention, 16-bit all-to-all), "
+                                       + ("fused peer-memory kernels over NVLink" if args.fused else "NCCL over NVLink")) if shard
                                       else f"dp{world} independent MSAs, no collective",
                        "l2": "no explicit flush: per-step working set (>= 1.4 GB activations + 183 MB weights at "
                              "cfg2) exceeds the 126 MB L2"},
@@ -347,6 +350,9 @@ def main():
     ap.add_argument("--shard", action="store_true",
                     help="N > 1: ONE deep MSA sharded over the ranks (rows for tied row attention, columns for column "
                          "attention; NCCL all-reduce + all-to-all) -> strong scaling.  Default: independent MSAs, weak.")
+    ap.add_argument("--fused", action="store_true",
+                    help="with --shard: the peer-memory schedule (softmax pulling/pushing logits over NVLink, LayerNorm "
+                         "pushing rows to the column owners, out-projection reducing into the row owners' residual)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

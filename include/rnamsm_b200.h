@@ -42,6 +42,7 @@ extern "C" {
 #define RNAMSM_ABI_VERSION 2
 
 enum { RNAMSM_F32 = 0, RNAMSM_BF16 = 1, RNAMSM_F16 = 2 };
+#define RNAMSM_MAX_PEERS 8 /* GPUs of one NVSwitch box a single MSA can be sharded over */
 
 /* Epilogues of rnamsm_linear. */
 enum {
@@ -196,6 +197,42 @@ int rnamsm_layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
 int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int R, int C, int has_pad, int dtype,
                        float* x, float* row_attn_out, float* const* rep_out, float* logits_out, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* ---- one deep MSA sharded over the GPUs of a box (rna-msm_b200/sharded.py) -----------
+ * The reference has no multi-GPU forward; these entry points implement the partition its math allows:
+ * rows for the tied row attention (sum of partial logits over ranks), columns for the column attention
+ * (it attends over rows, modules.py:907).  One process per GPU.  Buffers other GPUs touch come from
+ * rnamsm_peer_alloc and are mapped into the peers through CUDA IPC handles that the host exchanges
+ * (torch.distributed); the kernels below then read / write peer memory directly over NVLink.  Ordering
+ * between GPUs (a phase must have finished everywhere before the next reads its results) is the
+ * caller's job: a stream-ordered barrier between phases. */
+int rnamsm_peer_alloc(size_t bytes, void** out);            /* cudaMalloc, zero-filled, IPC-exportable */
+int rnamsm_peer_free(void* p);
+int rnamsm_ipc_export(const void* p, void* handle64);       /* 64-byte cudaIpcMemHandle_t */
+int rnamsm_ipc_import(const void* handle64, void** out);    /* maps a peer's buffer (enables peer access) */
+int rnamsm_ipc_close(void* p);
+
+/* LayerNorm of this rank's row shard x [Rn*C, D] (rows r0..r0+Rn of an R-row MSA) whose 16-bit output
+ * rows go straight into the column owners' buffers: token (r, c) -> peer_dst[c / (C/n)], row
+ * (c % (C/n)) * R + r, i.e. each peer ends with its column shard in [C/n, R, D] (column-major) order.
+ * Replaces LayerNorm + the row->column all-to-all. */
+int rnamsm_layernorm_push(const float* x, const float* w, const float* b, void* const* peer_dst, int n_ranks, int Rn,
+                          int C, int R, int r0, int D, float eps, int y_dtype, void* stream);
+
+/* Tied-logit exchange fused with K5: rank `rank` owns query rows [rank*C/n, (rank+1)*C/n); it pulls
+ * those rows of every rank's partial logits (peer_partial[g]: fp32 [n_splits, H, C, C]), sums them,
+ * applies logit_scale / key mask / softmax, writes the fp32 map rows into map_rank0 (a pointer into rank
+ * 0's [H, C, C] map, or NULL) and the 16-bit probabilities into every rank's peer_probs[g] [H, C, ld_lp].
+ * Replaces all-reduce + rnamsm_row_softmax. */
+int rnamsm_row_softmax_p2p(void* const* peer_partial, int n_ranks, int rank, int n_splits, int H, int C,
+                           const uint8_t* key_pad, float logit_scale, float* map_rank0, void* const* peer_probs,
+                           int ld_lp, int dtype, void* stream);
+
+/* Column block's out-projection fused with the column->row exchange and the residual add: ctx [R*Cn, K]
+ * (this rank's column shard c0..c0+Cn, token-major (r, c_local)) x W[N, K]^T + bias[N], reduce-added with
+ * TMA into peer_x[r / Rn] (fp32 [Rn*C, N]) at row (r % Rn) * C + c0 + c_local.  Cn % 16 == 0. */
+int rnamsm_linear_residual_scatter(const void* ctx, const void* W, const float* bias, int R, int Cn, int N, int K,
+                                   int dtype, void* const* peer_x, int n_ranks, int Rn, int C, int c0, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,14 @@ SIGNATURES = {
     "rnamsm_vocab_proj": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
     "rnamsm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "rnamsm_layer_forward": (_i, [C.POINTER(LayerWeights), _i, _i, _i, _f, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "rnamsm_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "rnamsm_peer_free": (_i, [_vp]),
+    "rnamsm_ipc_export": (_i, [_vp, _vp]),
+    "rnamsm_ipc_import": (_i, [_vp, C.POINTER(_vp)]),
+    "rnamsm_ipc_close": (_i, [_vp]),
+    "rnamsm_layernorm_push": (_i, [_vp, _vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "rnamsm_row_softmax_p2p": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _f, _vp, C.POINTER(_vp), _i, _i, _vp]),
+    "rnamsm_linear_residual_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_vp), _i, _i, _i, _i, _vp]),
     "rnamsm_msa_forward": (_i, [C.POINTER(ModelWeights), _vp, _i, _i, _i, _i, _vp, _vp, C.POINTER(_vp), _vp, _vp,
                                 _sz, _vp]),
 }

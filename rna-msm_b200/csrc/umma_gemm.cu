@@ -70,7 +70,13 @@ struct GemmArgs {
   const uint8_t* row_mask;
   void* out;             // TIED only (direct fp32 stores); the other variants store through tmap_out
   int ld_out;
+  // residual epilogue into PEER memory (sharded forward, column block's out-projection): output row
+  // m = r * Cn + c_local of this rank's column shard is reduce-added into row (r % Rn) * C + c0 + c_local
+  // of the fp32 residual stream of rank r / Rn, through that rank's tensor map.
+  int peer_n, peer_Rn, peer_Cn, peer_c0, peer_box_rows;
 };
+
+struct PeerMaps { CUtensorMap m[RNAMSM_MAX_PEERS]; };
 
 struct TileCoord {
   int m0, n0;            // element offsets of the PAIR tile inside the logical M / N extents
@@ -141,7 +147,8 @@ __device__ __forceinline__ void stage_row(uint8_t* buf, int lane, const uint32_t
 template <int kVariant>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g,
+                 const __grid_constant__ PeerMaps peers) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment (descriptor base_offset = 0).  The dynamic smem
   // window starts at the same offset in both CTAs, so the carve-up below is identical in the pair.
@@ -315,7 +322,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_reduce_add_3d(&tmap_out, buf, n, row0, 0);
+            if (kVariant == V_DENSE && g.peer_n > 0) {
+              // GEMM + column->row all-to-all + residual add in one: each sub-box of rows that share an
+              // MSA row goes to the residual stream of the rank owning that row, over NVLink
+              for (int sb = 0; sb < 32; sb += g.peer_box_rows) {
+                const int m = row0 + sb;
+                if (m >= g.M) break;
+                const int r = m / g.peer_Cn, cl = m - r * g.peer_Cn;
+                const int owner = r / g.peer_Rn;
+                tma_reduce_add_3d(&peers.m[owner], buf + sb * 128, n, g.peer_c0 + cl, r - owner * g.peer_Rn);
+              }
+            } else {
+              tma_reduce_add_3d(&tmap_out, buf, n, row0, 0);
+            }
             bulk_commit();
           }
         }
@@ -405,7 +424,7 @@ int g_max_pairs = 0;
 
 template <int kVariant>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g,
-                   int prof_class, cudaStream_t st) {
+                   int prof_class, cudaStream_t st, const PeerMaps* peers = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
     RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -433,7 +452,8 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   RNAMSM_REQUIRE(total > 0 && total < (1LL << 31), "umma_gemm: tile count %lld out of range", total);
   const int pairs = (int)std::min<long long>(total, g_max_pairs);
   ProfScope prof(prof_class, st);
-  umma_gemm_kernel<kVariant><<<2 * pairs, kThreads, kSmemBytes, st>>>(ta, tb, to, g);
+  static const PeerMaps no_peers{};
+  umma_gemm_kernel<kVariant><<<2 * pairs, kThreads, kSmemBytes, st>>>(ta, tb, to, g, peers ? *peers : no_peers);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -483,6 +503,50 @@ int launch_linear_16(const void* x, const void* W, long long M, int N, int K, in
   g.epi_kind = epi.kind; g.bias = epi.bias; g.q_scale = epi.q_scale; g.q_cols = epi.q_cols; g.row_mask = epi.row_mask;
   g.out = out; g.ld_out = N;
   return launch_variant<V_DENSE>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
+}
+
+// Column block's out-projection of the sharded forward: ctx [R*Cn, K] (this rank's column shard, token-major
+// (r, c_local)) x W[N, K]^T + bias, reduce-added into the row owners' residual streams (peer_x[g]: fp32
+// [Rn*C, N] on rank g).
+int launch_linear_16_scatter(const void* x, const void* W, const float* bias, int R, int Cn, int N, int K, int fp16,
+                             void* const* peer_x, int n_ranks, int Rn, int C, int c0, cudaStream_t st) {
+  const long long M = (long long)R * Cn;
+  RNAMSM_REQUIRE(M > 0 && M < (1LL << 31), "linear_scatter: M=%lld out of range", M);
+  RNAMSM_REQUIRE(N % 64 == 0 && K % BLOCK_K == 0 && K >= BLOCK_K, "linear_scatter: N=%d and K=%d must be multiples of 64", N, K);
+  RNAMSM_REQUIRE(n_ranks >= 1 && n_ranks <= RNAMSM_MAX_PEERS && Rn * n_ranks == R, "linear_scatter: R=%d != %d ranks x Rn=%d", R, n_ranks, Rn);
+  RNAMSM_REQUIRE(Cn % 16 == 0, "linear_scatter: columns per rank Cn=%d must be a multiple of 16 (TMA box rows)", Cn);
+  const int in_dt = fp16 ? TMAP_F16 : TMAP_BF16;
+  const int box_rows = Cn % 32 == 0 ? 32 : 16;
+  CUtensorMap ta, tb;
+  PeerMaps pm{};
+  {
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1};
+    uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)M * K * 2};
+    uint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+    if (encode_tmap(&ta, in_dt, x, 3, dims, strides, box)) return 3;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, 1};
+    uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)N * K * 2};
+    uint32_t box[3] = {BLOCK_K, HALF_N, 1};
+    if (encode_tmap(&tb, in_dt, W, 3, dims, strides, box)) return 3;
+  }
+  for (int g = 0; g < n_ranks; ++g) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)C, (uint64_t)Rn};
+    uint64_t strides[2] = {(uint64_t)N * 4, (uint64_t)C * N * 4};
+    uint32_t box[3] = {32, (uint32_t)box_rows, 1};
+    if (encode_tmap(&pm.m[g], TMAP_F32, peer_x[g], 3, dims, strides, box)) return 3;
+  }
+  GemmArgs g{};
+  g.m_tiles = ceil_div(M, PAIR_M);
+  g.n_tiles = ceil_div(N, BLOCK_N);
+  g.batches = 1; g.splits = 1;
+  g.k_blocks = K / BLOCK_K;
+  g.M = (int)M; g.N = N;
+  g.fp16 = fp16;
+  g.epi_kind = RNAMSM_EPI_BIAS_RESIDUAL; g.bias = bias; g.q_scale = 1.f;
+  g.peer_n = n_ranks; g.peer_Rn = Rn; g.peer_Cn = Cn; g.peer_c0 = c0; g.peer_box_rows = box_rows;
+  return launch_variant<V_DENSE>(ta, tb, pm.m[0], g, KC_LINEAR_OUT, st, &pm);
 }
 
 int gemm_max_pairs() { return g_max_pairs; }

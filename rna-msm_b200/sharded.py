@@ -248,13 +248,226 @@ class CudaShardOps:
                                        float(ln.eps), 0, 0, L.stream_ptr()), "layernorm")
 
 
+_FUSED_CACHE = {}
+
+
 def sharded_forward(model, tokens: torch.Tensor, group=None, need_head_weights: bool = True,
-                    gather_rows: bool = False) -> Dict[str, object]:
+                    gather_rows: bool = False, fused: bool = False) -> Dict[str, object]:
     """Convenience: run ``model`` (an eval-mode ``MSATransformer`` replicated on every rank's GPU) on one
-    MSA sharded over ``group``."""
+    MSA sharded over ``group``.  ``fused=True`` selects the peer-memory schedule (16-bit path)."""
     L = __import__("rnamsm_b200")._lib
     L.require_cuda(tokens, "tokens")
     L.device_check(tokens.device)
     with torch.cuda.device(tokens.device):
+        if fused:
+            key = (id(model), id(group))
+            if key not in _FUSED_CACHE:
+                _FUSED_CACHE[key] = FusedShardedForward(model, group)
+            return _FUSED_CACHE[key].forward(tokens, need_head_weights=need_head_weights, pad_idx=model.vocab.pad_idx)
         return ShardedMSAForward(CudaShardOps(model), model.num_layers, group).forward(
             tokens, need_head_weights=need_head_weights, gather_rows=gather_rows, pad_idx=model.vocab.pad_idx)
+
+
+# =====================================================================================================
+# Fused peer-memory schedule: the three exchanges above without NCCL on the data path
+# =====================================================================================================
+class PeerBuffer:
+    """A device buffer every rank of the group can address: allocated by librnamsm_b200 (cudaMalloc),
+    exported as a CUDA IPC handle, handles all-gathered over torch.distributed, peers' buffers mapped."""
+
+    def __init__(self, nbytes: int, group=None):
+        import ctypes as C
+        from . import _lib as L
+        self.L, self.C = L, C
+        self.nbytes = max(int(nbytes), 256)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        own = C.c_void_p()
+        L.check(L.lib.rnamsm_peer_alloc(self.nbytes, C.byref(own)), "peer_alloc")
+        self.own = own.value
+        self._imported = []
+        ptrs = [None] * self.world
+        ptrs[self.rank] = self.own
+        if self.world > 1:
+            handle = (C.c_ubyte * 64)()
+            L.check(L.lib.rnamsm_ipc_export(self.own, handle), "ipc_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            for g, h in enumerate(handles):
+                if g == self.rank:
+                    continue
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                p = C.c_void_p()
+                L.check(L.lib.rnamsm_ipc_import(buf, C.byref(p)), "ipc_import")
+                ptrs[g] = p.value
+                self._imported.append(p.value)
+        self.ptrs = ptrs
+        self.ptr_array = (C.c_void_p * self.world)(*ptrs)
+
+    def offset_array(self, byte_offset: int):
+        """void*[n] of every rank's buffer + byte_offset."""
+        return (self.C.c_void_p * self.world)(*[p + byte_offset for p in self.ptrs])
+
+    def tensor(self, dtype: torch.dtype, shape, byte_offset: int = 0) -> torch.Tensor:
+        """This rank's own memory as a torch tensor (no copy)."""
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        assert byte_offset + nbytes <= self.nbytes
+
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.own + byte_offset, False),
+                                      "version": 2}
+        t = torch.as_tensor(h, device="cuda")
+        t._rnamsm_keepalive = (h, self)
+        return t.view(dtype).view(*shape)
+
+    def close(self):
+        L = self.L
+        for p in self._imported:
+            L.lib.rnamsm_ipc_close(p)
+        self._imported = []
+        if self.own:
+            L.lib.rnamsm_peer_free(self.own)
+            self.own = None
+
+
+class FusedShardedForward:
+    """Same partition as ShardedMSAForward, 16-bit path only, with the exchanges fused into kernels that
+    address peer memory over NVLink (csrc/peer.cu, umma_gemm.cu):
+
+        tied logits    rnamsm_row_softmax_p2p : pull owned query rows of every rank's partial logits, softmax,
+                                                push 16-bit rows to all ranks + fp32 map rows to rank 0
+        row -> column  rnamsm_layernorm_push  : LayerNorm rows stored straight into the column owner's
+                                                [C/n, R, D] buffer
+        column -> row  rnamsm_linear_residual_scatter : out-projection GEMM whose epilogue TMA-reduce-adds
+                                                into the row owner's fp32 residual stream
+
+    Between phases: one stream-ordered 4-byte NCCL all-reduce as the cross-GPU barrier (4 per layer).
+    ``row_attentions`` is complete on rank 0 (the rank that owns MSA row 0 and writes the files)."""
+
+    def __init__(self, model, group=None):
+        from . import _lib as L
+        from .modules import _linear
+        self.L, self._linear, self.m, self.group = L, _linear, model, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > L_MAX_PEERS:
+            raise ValueError(f"at most {L_MAX_PEERS} ranks")
+        self.code, self.row_code = model._code, model._row_code
+        if self.code == L.F32:
+            raise ValueError("the fused peer-memory schedule exists for the 16-bit path; use ShardedMSAForward for fp32")
+        self.ops = CudaShardOps(model)
+        self._bufs = {}
+        self._flag = None
+
+    def _barrier(self):
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def _buffers(self, R, C, N):
+        key = (R, C, N)
+        if key in self._bufs:
+            return self._bufs[key]
+        for old in self._bufs.values():
+            for b in old["all"]:
+                b.close()
+        self._bufs = {}
+        L, n = self.L, self.world
+        D, H = self.m.embed_dim, self.m.num_attention_heads
+        Rn, Cn = R // n, C // n
+        splits = L.lib.rnamsm_row_attn_splits(Rn, C, H, self.row_code)
+        ldp = (C + 7) // 8 * 8
+        b = {
+            "x": PeerBuffer(Rn * C * D * 4, self.group),
+            "xn_cols": PeerBuffer(Cn * R * D * 2, self.group),
+            "partial": PeerBuffer(splits * H * C * C * 4, self.group),
+            "probs": PeerBuffer(H * C * ldp * 2, self.group),
+            "maps": PeerBuffer(N * H * C * C * 4 if self.rank == 0 else 256, self.group),
+        }
+        b["all"] = list(b.values())
+        b["splits"], b["ldp"] = splits, ldp
+        self._bufs[key] = b
+        return b
+
+    @torch.no_grad()
+    def forward(self, tokens: torch.Tensor, need_head_weights: bool = True, pad_idx: int = 1) -> Dict[str, object]:
+        import ctypes as Ct
+        L, m, ops = self.L, self.m, self.ops
+        assert tokens.ndim == 3 and tokens.shape[0] == 1, "one MSA per call: tokens [1, R, C]"
+        _, R, C = tokens.shape
+        plan = ShardPlan(R, C, self.world, self.rank)
+        n, Rn, Cn, g = plan.world, plan.Rn, plan.Cn, plan.rank
+        N, D, H = m.num_layers, m.embed_dim, m.num_attention_heads
+        if Cn % 16:
+            raise ValueError(f"fused schedule needs C / ranks = {Cn} to be a multiple of 16 (TMA box rows)")
+        code, row_code = self.code, self.row_code
+        dt, row_dt = L.torch_dtype(code), L.torch_dtype(row_code)
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.float32, device=tokens.device)
+        B = self._buffers(R, C, N)
+        splits, ldp = B["splits"], B["ldp"]
+        x = B["x"].tensor(torch.float32, (Rn * C, D))
+        xn_cols = B["xn_cols"].tensor(dt, (Cn * R, D))
+        partial = B["partial"].tensor(torch.float32, (splits, H, C, C))
+        probs = B["probs"].tensor(row_dt, (H, C, ldp))
+        maps = B["maps"].tensor(torch.float32, (N, H, C, C)) if (g == 0 and need_head_weights) else None
+        st = L.stream_ptr()
+
+        tok = tokens[0]
+        pad_full = tok.eq(pad_idx)
+        has_pad = bool(pad_full.any())
+        pad_rows = CudaShardOps._u8(pad_full[plan.rows()]) if has_pad else None
+        pad_cols = CudaShardOps._u8(pad_full[:, plan.cols()]) if has_pad else None
+        key_pad = CudaShardOps._u8(pad_full[0]) if has_pad else None
+
+        x.copy_(ops.embed(tok[plan.rows()].contiguous(), plan.r0, R))
+        self._barrier()                                   # every rank's buffers are initialised
+        logit_scale = 1.0 / math.sqrt(R)
+        for l in range(N):
+            layer = m.layers[l]
+            # ---- tied row attention ------------------------------------------------------------------
+            blk = layer.row_self_attention
+            w_qkv, b_qkv, w_out, b_out = blk.layer._pack(row_code)
+            xn = ops._ln(x, blk.layer_norm, row_code, Rn * C)
+            qkv = self._linear(xn, w_qkv, b_qkv, row_code, L.EPI_BIAS, 0.125, D, pad_rows)
+            L.check(L.lib.rnamsm_row_attn_logits(L.ptr(qkv), Rn, C, H, row_code, L.ptr(partial), splits, st), "row_attn_logits")
+            self._barrier()                               # all partial logits written
+            map_ptr = None
+            if need_head_weights:                         # rank 0's map slab of this layer (peer pointer)
+                map_ptr = B["maps"].ptrs[0] + l * H * C * C * 4
+            L.check(L.lib.rnamsm_row_softmax_p2p(B["partial"].ptr_array, n, g, splits, H, C, L.ptr(key_pad),
+                                                 float(logit_scale), map_ptr, B["probs"].ptr_array, ldp, row_code, st),
+                    "row_softmax_p2p")
+            self._barrier()                               # every rank's probabilities complete
+            ctx = torch.empty((Rn * C, D), dtype=row_dt, device=x.device)
+            L.check(L.lib.rnamsm_row_attn_av(L.ptr(probs), ldp, L.ptr(qkv), Rn, C, H, row_code, L.ptr(ctx), st), "row_attn_av")
+            self._linear(ctx, w_out, b_out, row_code, L.EPI_BIAS_RESIDUAL, out=x)
+            # ---- column attention ----------------------------------------------------------------------
+            blk = layer.column_self_attention
+            w_qkv, b_qkv, w_out, b_out = blk.layer._pack(code)
+            ln = blk.layer_norm
+            L.check(L.lib.rnamsm_layernorm_push(L.ptr(x), L.ptr(ln.weight), L.ptr(ln.bias), B["xn_cols"].ptr_array, n, Rn, C,
+                                                R, plan.r0, D, float(ln.eps), code, st), "layernorm_push")
+            self._barrier()                               # this rank's column shard has arrived
+            qkv_c = self._linear(xn_cols, w_qkv, b_qkv, code, L.EPI_BIAS, 0.125, D, None)       # [Cn, R, 3D]
+            ctx_c = torch.empty((R * Cn, D), dtype=dt, device=x.device)                          # token-major [R, Cn, D]
+            L.check(L.lib.rnamsm_col_attn(L.ptr(qkv_c), R, Cn, H, code, 1, L.ptr(pad_cols), L.ptr(ctx_c), st), "col_attn")
+            L.check(L.lib.rnamsm_linear_residual_scatter(L.ptr(ctx_c), L.ptr(w_out), L.ptr(b_out), R, Cn, D, D, code,
+                                                         B["x"].ptr_array, n, Rn, C, plan.c0, st), "linear_residual_scatter")
+            self._barrier()                               # every contribution has landed in x
+            # ---- feed-forward ----------------------------------------------------------------------------
+            ops.ffn(l, x, Rn * C)
+        ops.final_ln(x, Rn * C)
+        out: Dict[str, object] = {"logits": None, "representations": {N: x.view(1, Rn, C, D)},
+                                  "row_shard": (plan.r0, plan.r0 + Rn)}
+        if maps is not None:
+            self._barrier()
+            out["row_attentions"] = maps.view(1, N, H, C, C)
+        return out
+
+
+L_MAX_PEERS = 8

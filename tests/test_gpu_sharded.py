@@ -40,6 +40,20 @@ def test_world1_matches_model_forward(precision, pads):
     assert O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"].cpu()) < tol
 
 
+@pytest.mark.parametrize("pads", [(0, 0), (3, 2)], ids=["nopad", "pad"])
+def test_world1_fused_matches_model_forward(pads):
+    """The peer-memory kernels (softmax_p2p, layernorm_push, residual scatter) with a single rank."""
+    import rnamsm_b200 as pkg
+    from rnamsm_b200.sharded import sharded_forward
+    m = _model(pkg, 3, "fp16", "cuda")
+    tokens = O.make_tokens(40, 80, 4, pad_cols=pads[0], pad_rows=pads[1]).cuda()
+    ref = m(tokens, repr_layers=[3], need_head_weights=True, want_logits=False)
+    out = sharded_forward(m, tokens, fused=True)
+    torch.cuda.synchronize()
+    assert O.rel_err(out["representations"][3].cpu(), ref["representations"][3].cpu()) < 2e-3
+    assert O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"].cpu()) < 2e-3
+
+
 def _worker(rank, world, port, precision, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -53,8 +67,16 @@ def _worker(rank, world, port, precision, q):
         ref = m(tokens, repr_layers=[3], need_head_weights=True, want_logits=False)
         out = sharded_forward(m, tokens, gather_rows=True)
         torch.cuda.synchronize()
-        q.put((rank, O.rel_err(out["representations"][3].cpu(), ref["representations"][3].cpu()),
-               O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"].cpu())))
+        errs = [O.rel_err(out["representations"][3].cpu(), ref["representations"][3].cpu()),
+                O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"].cpu())]
+        if precision == "fp16":                    # fused peer-memory schedule: row shard + maps on rank 0
+            fo = sharded_forward(m, tokens, fused=True)
+            torch.cuda.synchronize()
+            r0, r1 = fo["row_shard"]
+            errs.append(O.rel_err(fo["representations"][3].cpu(), ref["representations"][3][:, r0:r1].cpu()))
+            if rank == 0:
+                errs.append(O.rel_err(fo["row_attentions"].cpu(), ref["row_attentions"].cpu()))
+        q.put((rank, max(errs[:1] + errs[2:3]), max(errs[1:2] + errs[3:])))
     finally:
         dist.destroy_process_group()
 
