@@ -464,8 +464,9 @@ class FusedShardedForward:
         ops.final_ln(x, Rn * C)
         out: Dict[str, object] = {"logits": None, "representations": {N: x.view(1, Rn, C, D)},
                                   "row_shard": (plan.r0, plan.r0 + Rn)}
+        if need_head_weights:
+            self._barrier()                               # (all ranks) the last layer's map rows have reached rank 0
         if maps is not None:
-            self._barrier()
             out["row_attentions"] = maps.view(1, N, H, C, C)
         return out
 
