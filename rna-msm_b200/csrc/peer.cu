@@ -151,6 +151,89 @@ row_softmax_p2p_kernel(PeerPtrs partial, int n_ranks, int n_splits, int H, int C
   }
 }
 
+// Block-per-row, 128-bit version for C % 4 == 0 (every production shape): 128 threads own one (head,
+// query row), thread t holds columns 4t + 512k.  All remote float4 loads of a row are issued before
+// the first use (NVLink latency ~2 us), the fp32 map row leaves as float4 stores to rank 0, the 16-bit
+// row as 8-byte stores to every rank.
+constexpr int kP2pT = 8;   // C <= 512 * kP2pT
+
+template <int kLp>
+__global__ void __launch_bounds__(128)
+row_softmax_p2p_vec_kernel(PeerPtrs partial, int n_ranks, int n_splits, int H, int C, int i0, int rows_owned,
+                           const uint8_t* __restrict__ key_pad, float logit_scale, float* map_rank0, PeerPtrs probs,
+                           int ld_lp) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x / rows_owned, i = i0 + blockIdx.x % rows_owned;
+  const size_t row_off = ((size_t)h * C + i) * C;
+  const size_t split_stride = (size_t)H * C * C;
+  float acc[kP2pT][4];
+#pragma unroll
+  for (int k = 0; k < kP2pT; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[k][e] = 0.f;
+  for (int g = 0; g < n_ranks; ++g) {
+    const float* src = reinterpret_cast<const float*>(partial.p[g]) + row_off;
+    for (int s = 0; s < n_splits; ++s) {
+#pragma unroll
+      for (int k = 0; k < kP2pT; ++k) {
+        const int j = 4 * tid + 512 * k;
+        if (j < C) {
+          const float4 v = *reinterpret_cast<const float4*>(src + s * split_stride + j);
+          acc[k][0] += v.x; acc[k][1] += v.y; acc[k][2] += v.z; acc[k][3] += v.w;
+        }
+      }
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kP2pT; ++k) {
+    const int j = 4 * tid + 512 * k;
+    if (j < C) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = acc[k][e] * logit_scale;
+        if (key_pad && key_pad[j + e]) a = -10000.f;                  // masked_fill, modules.py:780-784
+        acc[k][e] = a;
+        mx = fmaxf(mx, a);
+      }
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kP2pT; ++k) {
+    const int j = 4 * tid + 512 * k;
+    if (j < C) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { acc[k][e] = __expf(acc[k][e] - mx); sum += acc[k][e]; }
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[4 + warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / ((red[4] + red[5]) + (red[6] + red[7]));
+  const size_t lp_off = ((size_t)h * C + i) * ld_lp;
+#pragma unroll
+  for (int k = 0; k < kP2pT; ++k) {
+    const int j = 4 * tid + 512 * k;
+    if (j < C) {
+      const float4 p = make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
+      if (map_rank0) *reinterpret_cast<float4*>(map_rank0 + row_off + j) = p;
+      const uint2 pk = kLp == 1 ? make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w))
+                                : make_uint2(pack_f16(p.x, p.y), pack_f16(p.z, p.w));
+      for (int g = 0; g < n_ranks; ++g)
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(probs.p[g]) + lp_off + j) = pk;
+    } else if (j < ld_lp) {                                           // zero the padding columns [C, ld_lp)
+      for (int g = 0; g < n_ranks; ++g)
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(probs.p[g]) + lp_off + j) = make_uint2(0u, 0u);
+    }
+  }
+}
+
 }  // namespace rnamsm
 
 using namespace rnamsm;
@@ -224,6 +307,17 @@ int rnamsm_row_softmax_p2p(void* const* peer_partial, int n_ranks, int rank, int
   const int blocks = (int)((rows + 3) / 4);
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(KC_ROW_SOFTMAX, st);
+  if (C % 4 == 0 && C <= 512 * kP2pT && ld_lp % 4 == 0) {
+    if (dtype == RNAMSM_BF16)
+      row_softmax_p2p_vec_kernel<1><<<(int)rows, 128, 0, st>>>(pp, n_ranks, n_splits, H, C, i0, Cq, key_pad, logit_scale,
+                                                            map_rank0, pr, ld_lp);
+    else
+      row_softmax_p2p_vec_kernel<2><<<(int)rows, 128, 0, st>>>(pp, n_ranks, n_splits, H, C, i0, Cq, key_pad, logit_scale,
+                                                            map_rank0, pr, ld_lp);
+    count_launch();
+    RNAMSM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (dtype == RNAMSM_BF16)
     row_softmax_p2p_kernel<1><<<blocks, 128, 0, st>>>(pp, n_ranks, n_splits, H, C, i0, i1, key_pad, logit_scale, map_rank0, pr, ld_lp);
   else
