@@ -228,11 +228,22 @@ int rnamsm_row_softmax_p2p(void* const* peer_partial, int n_ranks, int rank, int
                            const uint8_t* key_pad, float logit_scale, float* map_rank0, void* const* peer_probs,
                            int ld_lp, int dtype, void* stream);
 
-/* Column block's out-projection fused with the column->row exchange and the residual add: ctx [R*Cn, K]
- * (this rank's column shard c0..c0+Cn, token-major (r, c_local)) x W[N, K]^T + bias[N], reduce-added with
- * TMA into peer_x[r / Rn] (fp32 [Rn*C, N]) at row (r % Rn) * C + c0 + c_local.  Cn % 16 == 0. */
+/* Column block's out-projection fused with the column->row exchange: ctx [R*Cn, K] (this rank's column
+ * shard c0..c0+Cn, token-major (r, c_local)) x W[N, K]^T + bias[N], delivered to rank r / Rn at row
+ * (r % Rn) * C + c0 + c_local of peer_x[r / Rn] ([Rn*C, N]):
+ *   as_delta16 = 0: peer_x are the fp32 residual streams, the epilogue TMA-reduce-adds into them
+ *                   (GEMM + exchange + residual add in one kernel; 4 bytes per element over NVLink);
+ *   as_delta16 = 1: peer_x are 16-bit receive buffers, the epilogue TMA-stores the result (2 bytes per
+ *                   element); the owner adds it with rnamsm_add_layernorm on its next LayerNorm pass.
+ * Cn % 16 == 0. */
 int rnamsm_linear_residual_scatter(const void* ctx, const void* W, const float* bias, int R, int Cn, int N, int K,
-                                   int dtype, void* const* peer_x, int n_ranks, int Rn, int C, int c0, void* stream);
+                                   int dtype, void* const* peer_x, int n_ranks, int Rn, int C, int c0, int as_delta16,
+                                   void* stream);
+
+/* x (fp32, in place) += delta (16-bit); y = LayerNorm(x) in 16 bits: the residual add of a contribution
+ * that arrived in a receive buffer, fused into the LayerNorm that reads x next (modules.py:385-401). */
+int rnamsm_add_layernorm(float* x, const void* delta, int delta_dtype, const float* w, const float* b, void* y,
+                         int y_dtype, long long n_rows, int D, float eps, void* stream);
 
 #ifdef __cplusplus
 }

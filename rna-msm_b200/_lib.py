@@ -68,7 +68,8 @@ SIGNATURES = {
     "rnamsm_ipc_close": (_i, [_vp]),
     "rnamsm_layernorm_push": (_i, [_vp, _vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "rnamsm_row_softmax_p2p": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _f, _vp, C.POINTER(_vp), _i, _i, _vp]),
-    "rnamsm_linear_residual_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_vp), _i, _i, _i, _i, _vp]),
+    "rnamsm_linear_residual_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_vp), _i, _i, _i, _i, _i, _vp]),
+    "rnamsm_add_layernorm": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _ll, _i, _f, _vp]),
     "rnamsm_msa_forward": (_i, [C.POINTER(ModelWeights), _vp, _i, _i, _i, _i, _vp, _vp, C.POINTER(_vp), _vp, _vp,
                                 _sz, _vp]),
 }

@@ -1,6 +1,8 @@
 // HBM-bound kernels of the RNA-MSM forward: embedding gather + LayerNorm (K1), LayerNorm (K2/K9),
 // tied-attention softmax / map export (K5) and the 12-wide tied LM-head projection (K9b).
 // All are one-warp-per-row, 128-bit vectorised, fp32 statistics.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -149,6 +151,50 @@ layernorm_kernel(const float* x, const float* __restrict__ w, const float* __res
 }
 
 // -------------------------------------------------------------------------------------------
+// x += delta (16-bit contribution of a block computed elsewhere, e.g. the column block of the sharded
+// forward), x written back in fp32, and LayerNorm(x) written in 16 bits for the next GEMM: the residual
+// add rides on the LayerNorm pass that reads x anyway.  kDelta / kOut: 1 = bf16, 2 = fp16.
+// -------------------------------------------------------------------------------------------
+template <int kDelta, int kOut>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_layernorm_kernel(float* __restrict__ x, const uint16_t* __restrict__ delta, const float* __restrict__ w,
+                     const float* __restrict__ b, uint16_t* __restrict__ y, long long n_rows, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = D / 128;
+  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < n_rows; row += (long long)gridDim.x * kLnWarps) {
+    float* xr = x + (size_t)row * D;
+    const uint16_t* dr = delta + (size_t)row * D;
+    float4 v[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const int f = lane * 4 + i * 128;
+        v[i] = *reinterpret_cast<const float4*>(xr + f);
+        const uint2 d2 = *reinterpret_cast<const uint2*>(dr + f);
+        float d0, d1, d2f, d3;
+        if (kDelta == 1) {
+          d0 = __uint_as_float(d2.x << 16); d1 = __uint_as_float(d2.x & 0xffff0000u);
+          d2f = __uint_as_float(d2.y << 16); d3 = __uint_as_float(d2.y & 0xffff0000u);
+        } else {
+          const __half2 h0 = *reinterpret_cast<const __half2*>(&d2.x), h1 = *reinterpret_cast<const __half2*>(&d2.y);
+          d0 = __low2float(h0); d1 = __high2float(h0); d2f = __low2float(h1); d3 = __high2float(h1);
+        }
+        v[i].x += d0; v[i].y += d1; v[i].z += d2f; v[i].w += d3;
+        *reinterpret_cast<float4*>(xr + f) = v[i];
+      }
+    warp_layernorm(v, nv, D, eps, w, b, lane);
+    uint16_t* dst = y + (size_t)row * D;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const uint2 pk = kOut == 1 ? make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w))
+                                   : make_uint2(pack_f16(v[i].x, v[i].y), pack_f16(v[i].z, v[i].w));
+        *reinterpret_cast<uint2*>(dst + lane * 4 + i * 128) = pk;
+      }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // K5: one warp per (head, query column i).  Sums the split-K partial logits, applies the key
 // mask, softmax over j, writes the fp32 map (the exported attention map) and the low-precision
 // copy that feeds the AV GEMM.  Three passes over the (L2-resident) partial rows keep register
@@ -258,6 +304,24 @@ int launch_layernorm(const float* x, const float* w, const float* b, void* y, in
     layernorm_kernel<2><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
   else
     layernorm_kernel<0><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
+  count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_add_layernorm(float* x, const void* delta, int delta_dtype, const float* w, const float* b, void* y,
+                         int y_dtype, long long n_rows, int D, float eps, cudaStream_t st) {
+  RNAMSM_REQUIRE(D % 128 == 0 && D <= 128 * kMaxVec, "add_layernorm: D=%d must be a multiple of 128 <= 1024", D);
+  RNAMSM_REQUIRE((delta_dtype == 1 || delta_dtype == 2) && (y_dtype == 1 || y_dtype == 2), "add_layernorm: 16-bit delta / output only");
+  if (n_rows <= 0) return 0;
+  const int blocks = (int)std::min<long long>((n_rows + kLnWarps - 1) / kLnWarps, 148LL * 32);
+  ProfScope prof(KC_LAYERNORM, st);
+  const uint16_t* d = reinterpret_cast<const uint16_t*>(delta);
+  uint16_t* yy = reinterpret_cast<uint16_t*>(y);
+  if (delta_dtype == 1 && y_dtype == 1) add_layernorm_kernel<1, 1><<<blocks, kLnWarps * 32, 0, st>>>(x, d, w, b, yy, n_rows, D, eps);
+  else if (delta_dtype == 1) add_layernorm_kernel<1, 2><<<blocks, kLnWarps * 32, 0, st>>>(x, d, w, b, yy, n_rows, D, eps);
+  else if (y_dtype == 1) add_layernorm_kernel<2, 1><<<blocks, kLnWarps * 32, 0, st>>>(x, d, w, b, yy, n_rows, D, eps);
+  else add_layernorm_kernel<2, 2><<<blocks, kLnWarps * 32, 0, st>>>(x, d, w, b, yy, n_rows, D, eps);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -68,7 +68,9 @@ int launch_row_av_16(const void* probs, int ldp, const void* qkv, int R, int C, 
 int row_logits_splits_16(int R, int C, int H);
 int gemm_max_pairs();
 int launch_linear_16_scatter(const void* x, const void* W, const float* bias, int R, int Cn, int N, int K, int fp16,
-                             void* const* peer_x, int n_ranks, int Rn, int C, int c0, cudaStream_t st);
+                             void* const* peer_x, int n_ranks, int Rn, int C, int c0, int as_delta16, cudaStream_t st);
+int launch_add_layernorm(float* x, const void* delta, int delta_dtype, const float* w, const float* b, void* y,
+                         int y_dtype, long long n_rows, int D, float eps, cudaStream_t st);
 
 // col_attn_umma.cu
 int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,

@@ -288,10 +288,16 @@ int rnamsm_layernorm_push(const float* x, const float* w, const float* b, void* 
 }
 
 int rnamsm_linear_residual_scatter(const void* ctx, const void* W, const float* bias, int R, int Cn, int N, int K,
-                                   int dtype, void* const* peer_x, int n_ranks, int Rn, int C, int c0, void* stream) {
+                                   int dtype, void* const* peer_x, int n_ranks, int Rn, int C, int c0, int as_delta16,
+                                   void* stream) {
   RNAMSM_REQUIRE(dtype == RNAMSM_BF16 || dtype == RNAMSM_F16, "linear_residual_scatter: 16-bit operands only");
-  return launch_linear_16_scatter(ctx, W, bias, R, Cn, N, K, dtype == RNAMSM_F16, peer_x, n_ranks, Rn, C, c0,
+  return launch_linear_16_scatter(ctx, W, bias, R, Cn, N, K, dtype == RNAMSM_F16, peer_x, n_ranks, Rn, C, c0, as_delta16,
                                   (cudaStream_t)stream);
+}
+
+int rnamsm_add_layernorm(float* x, const void* delta, int delta_dtype, const float* w, const float* b, void* y,
+                         int y_dtype, long long n_rows, int D, float eps, void* stream) {
+  return launch_add_layernorm(x, delta, delta_dtype, w, b, y, y_dtype, n_rows, D, eps, (cudaStream_t)stream);
 }
 
 int rnamsm_row_softmax_p2p(void* const* peer_partial, int n_ranks, int rank, int n_splits, int H, int C,

@@ -390,7 +390,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmap_out, buf, c0, c1, c2);
+            if (kVariant == V_DENSE && g.peer_n > 0) {
+              // 16-bit result rows stored into the row owners' receive buffers over NVLink (half the bytes
+              // of the fp32 reduce; the add happens in the owner's next LayerNorm pass)
+              for (int sb = 0; sb < 32; sb += g.peer_box_rows) {
+                const int m = c1 + sb;
+                if (m >= g.M) break;
+                const int r = m / g.peer_Cn, cl = m - r * g.peer_Cn;
+                const int owner = r / g.peer_Rn;
+                tma_store_3d(&peers.m[owner], buf + sb * 128, c0, g.peer_c0 + cl, r - owner * g.peer_Rn);
+              }
+            } else {
+              tma_store_3d(&tmap_out, buf, c0, c1, c2);
+            }
             bulk_commit();
           }
         }
@@ -509,7 +521,7 @@ int launch_linear_16(const void* x, const void* W, long long M, int N, int K, in
 // (r, c_local)) x W[N, K]^T + bias, reduce-added into the row owners' residual streams (peer_x[g]: fp32
 // [Rn*C, N] on rank g).
 int launch_linear_16_scatter(const void* x, const void* W, const float* bias, int R, int Cn, int N, int K, int fp16,
-                             void* const* peer_x, int n_ranks, int Rn, int C, int c0, cudaStream_t st) {
+                             void* const* peer_x, int n_ranks, int Rn, int C, int c0, int as_delta16, cudaStream_t st) {
   const long long M = (long long)R * Cn;
   RNAMSM_REQUIRE(M > 0 && M < (1LL << 31), "linear_scatter: M=%lld out of range", M);
   RNAMSM_REQUIRE(N % 64 == 0 && K % BLOCK_K == 0 && K >= BLOCK_K, "linear_scatter: N=%d and K=%d must be multiples of 64", N, K);
@@ -531,11 +543,12 @@ int launch_linear_16_scatter(const void* x, const void* W, const float* bias, in
     uint32_t box[3] = {BLOCK_K, HALF_N, 1};
     if (encode_tmap(&tb, in_dt, W, 3, dims, strides, box)) return 3;
   }
-  for (int g = 0; g < n_ranks; ++g) {
+  for (int g = 0; g < n_ranks; ++g) {       // peer_x[g]: fp32 residual [Rn*C, N], or 16-bit receive buffer of the same shape
+    const uint64_t el = as_delta16 ? 2 : 4;
     uint64_t dims[3] = {(uint64_t)N, (uint64_t)C, (uint64_t)Rn};
-    uint64_t strides[2] = {(uint64_t)N * 4, (uint64_t)C * N * 4};
-    uint32_t box[3] = {32, (uint32_t)box_rows, 1};
-    if (encode_tmap(&pm.m[g], TMAP_F32, peer_x[g], 3, dims, strides, box)) return 3;
+    uint64_t strides[2] = {(uint64_t)N * el, (uint64_t)C * N * el};
+    uint32_t box[3] = {as_delta16 ? 64u : 32u, (uint32_t)box_rows, 1};
+    if (encode_tmap(&pm.m[g], as_delta16 ? in_dt : TMAP_F32, peer_x[g], 3, dims, strides, box)) return 3;
   }
   GemmArgs g{};
   g.m_tiles = ceil_div(M, PAIR_M);
@@ -544,7 +557,7 @@ int launch_linear_16_scatter(const void* x, const void* W, const float* bias, in
   g.k_blocks = K / BLOCK_K;
   g.M = (int)M; g.N = N;
   g.fp16 = fp16;
-  g.epi_kind = RNAMSM_EPI_BIAS_RESIDUAL; g.bias = bias; g.q_scale = 1.f;
+  g.epi_kind = as_delta16 ? RNAMSM_EPI_BIAS : RNAMSM_EPI_BIAS_RESIDUAL; g.bias = bias; g.q_scale = 1.f;
   g.peer_n = n_ranks; g.peer_Rn = Rn; g.peer_Cn = Cn; g.peer_c0 = c0; g.peer_box_rows = box_rows;
   return launch_variant<V_DENSE>(ta, tb, pm.m[0], g, KC_LINEAR_OUT, st, &pm);
 }

@@ -343,8 +343,10 @@ class FusedShardedForward:
                                                 push 16-bit rows to all ranks + fp32 map rows to rank 0
         row -> column  rnamsm_layernorm_push  : LayerNorm rows stored straight into the column owner's
                                                 [C/n, R, D] buffer
-        column -> row  rnamsm_linear_residual_scatter : out-projection GEMM whose epilogue TMA-reduce-adds
-                                                into the row owner's fp32 residual stream
+        column -> row  rnamsm_linear_residual_scatter : out-projection GEMM whose epilogue TMA-stores the 16-bit
+                                                result into the row owner's receive buffer (or TMA-reduce-adds
+                                                fp32 into its residual stream); rnamsm_add_layernorm adds it
+                                                on the FFN's LayerNorm pass
 
     Between phases: one stream-ordered 4-byte NCCL all-reduce as the cross-GPU barrier (4 per layer).
     ``row_attentions`` is complete on rank 0 (the rank that owns MSA row 0 and writes the files)."""
@@ -363,6 +365,9 @@ class FusedShardedForward:
         self.ops = CudaShardOps(model)
         self._bufs = {}
         self._flag = None
+        import os
+        # column->row payload: 16-bit into a receive buffer (default) or fp32 TMA reduce-add straight into x
+        self.scatter_fp32 = os.environ.get("RNAMSM_SCATTER_FP32", "0") == "1"
 
     def _barrier(self):
         if self.world > 1:
@@ -387,6 +392,7 @@ class FusedShardedForward:
             "partial": PeerBuffer(splits * H * C * C * 4, self.group),
             "probs": PeerBuffer(H * C * ldp * 2, self.group),
             "maps": PeerBuffer(N * H * C * C * 4 if self.rank == 0 else 256, self.group),
+            "delta": PeerBuffer(Rn * C * D * 2, self.group),
         }
         b["all"] = list(b.values())
         b["splits"], b["ldp"] = splits, ldp
@@ -414,6 +420,7 @@ class FusedShardedForward:
         xn_cols = B["xn_cols"].tensor(dt, (Cn * R, D))
         partial = B["partial"].tensor(torch.float32, (splits, H, C, C))
         probs = B["probs"].tensor(row_dt, (H, C, ldp))
+        delta = B["delta"].tensor(dt, (Rn * C, D))
         maps = B["maps"].tensor(torch.float32, (N, H, C, C)) if (g == 0 and need_head_weights) else None
         st = L.stream_ptr()
 
@@ -456,11 +463,26 @@ class FusedShardedForward:
             qkv_c = self._linear(xn_cols, w_qkv, b_qkv, code, L.EPI_BIAS, 0.125, D, None)       # [Cn, R, 3D]
             ctx_c = torch.empty((R * Cn, D), dtype=dt, device=x.device)                          # token-major [R, Cn, D]
             L.check(L.lib.rnamsm_col_attn(L.ptr(qkv_c), R, Cn, H, code, 1, L.ptr(pad_cols), L.ptr(ctx_c), st), "col_attn")
+            if self.scatter_fp32:
+                L.check(L.lib.rnamsm_linear_residual_scatter(L.ptr(ctx_c), L.ptr(w_out), L.ptr(b_out), R, Cn, D, D, code,
+                                                             B["x"].ptr_array, n, Rn, C, plan.c0, 0, st),
+                        "linear_residual_scatter")
+                self._barrier()                           # every contribution has been reduced into x
+                ops.ffn(l, x, Rn * C)
+                continue
             L.check(L.lib.rnamsm_linear_residual_scatter(L.ptr(ctx_c), L.ptr(w_out), L.ptr(b_out), R, Cn, D, D, code,
-                                                         B["x"].ptr_array, n, Rn, C, plan.c0, st), "linear_residual_scatter")
-            self._barrier()                               # every contribution has landed in x
-            # ---- feed-forward ----------------------------------------------------------------------------
-            ops.ffn(l, x, Rn * C)
+                                                         B["delta"].ptr_array, n, Rn, C, plan.c0, 1, st),
+                    "linear_residual_scatter")
+            self._barrier()                               # every column owner's 16-bit contribution has arrived
+            # ---- feed-forward (its LayerNorm pass also adds the column block's contribution to x) --------
+            blk = layer.feed_forward_layer
+            w1, b1, w2, b2 = blk.layer._pack(code)
+            ln = blk.layer_norm
+            xn_f = torch.empty((Rn * C, D), dtype=dt, device=x.device)
+            L.check(L.lib.rnamsm_add_layernorm(L.ptr(x), L.ptr(delta), code, L.ptr(ln.weight), L.ptr(ln.bias), L.ptr(xn_f),
+                                               code, Rn * C, D, float(ln.eps), st), "add_layernorm")
+            hdn = self._linear(xn_f, w1, b1, code, L.EPI_BIAS_GELU)
+            self._linear(hdn, w2, b2, code, L.EPI_BIAS_RESIDUAL, out=x)
         ops.final_ln(x, Rn * C)
         out: Dict[str, object] = {"logits": None, "representations": {N: x.view(1, Rn, C, D)},
                                   "row_shard": (plan.r0, plan.r0 + Rn)}

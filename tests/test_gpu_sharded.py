@@ -41,10 +41,15 @@ def test_world1_matches_model_forward(precision, pads):
 
 
 @pytest.mark.parametrize("pads", [(0, 0), (3, 2)], ids=["nopad", "pad"])
-def test_world1_fused_matches_model_forward(pads):
-    """The peer-memory kernels (softmax_p2p, layernorm_push, residual scatter) with a single rank."""
+@pytest.mark.parametrize("scatter_fp32", ["0", "1"], ids=["delta16", "reduce32"])
+def test_world1_fused_matches_model_forward(pads, scatter_fp32, monkeypatch):
+    """The peer-memory kernels (softmax_p2p, layernorm_push, residual scatter in both payload modes,
+    add_layernorm) with a single rank."""
     import rnamsm_b200 as pkg
+    from rnamsm_b200 import sharded
     from rnamsm_b200.sharded import sharded_forward
+    monkeypatch.setenv("RNAMSM_SCATTER_FP32", scatter_fp32)
+    sharded._FUSED_CACHE.clear()
     m = _model(pkg, 3, "fp16", "cuda")
     tokens = O.make_tokens(40, 80, 4, pad_cols=pads[0], pad_rows=pads[1]).cuda()
     ref = m(tokens, repr_layers=[3], need_head_weights=True, want_logits=False)
