@@ -35,11 +35,17 @@ constexpr int kLnWarpsP = 8;
 template <int kOut>
 __global__ void __launch_bounds__(kLnWarpsP * 32)
 layernorm_push_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                      PeerPtrs dst, int Rn, int C, int Cn, int R, int r0, int D, float eps) {
+                      PeerPtrs dst, int Rn, int C, int Cn, int R, int r0, int D, float eps, int c_shift) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / 128;
   const long long n_rows = (long long)Rn * C;
-  for (long long row = (long long)blockIdx.x * kLnWarpsP + warp; row < n_rows; row += (long long)gridDim.x * kLnWarpsP) {
+  for (long long it = (long long)blockIdx.x * kLnWarpsP + warp; it < n_rows; it += (long long)gridDim.x * kLnWarpsP) {
+    // every rank walks the columns starting at its own shard (c_shift), so at any moment the ranks
+    // write to DIFFERENT column owners instead of all hitting the same one's NVLink ingress
+    const int r_it = (int)(it / C);
+    int c_it = (int)(it % C) + c_shift;
+    if (c_it >= C) c_it -= C;
+    const long long row = (long long)r_it * C + c_it;
     const float* src = x + (size_t)row * D;
     float4 v[kMaxVecP];
 #pragma unroll
@@ -79,7 +85,7 @@ layernorm_push_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 // One warp per (head, owned query row i).  partial slabs: [n_splits, H, C, C] fp32 on every rank.
 template <int kLp>
 __global__ void __launch_bounds__(128)
-row_softmax_p2p_kernel(PeerPtrs partial, int n_ranks, int n_splits, int H, int C, int i0, int i1,
+row_softmax_p2p_kernel(PeerPtrs partial, int n_ranks, int rank, int n_splits, int H, int C, int i0, int i1,
                        const uint8_t* __restrict__ key_pad, float logit_scale, float* map_rank0, PeerPtrs probs,
                        int ld_lp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,8 +97,8 @@ row_softmax_p2p_kernel(PeerPtrs partial, int n_ranks, int n_splits, int H, int C
   const size_t split_stride = (size_t)H * C * C;
   auto logit = [&](int j) -> float {
     float a = 0.f;
-    for (int g = 0; g < n_ranks; ++g) {
-      const float* src = reinterpret_cast<const float*>(partial.p[g]) + row_off;
+    for (int t = 1; t <= n_ranks; ++t) {            // start at the next rank: no two ranks pull from the same source at once
+      const float* src = reinterpret_cast<const float*>(partial.p[(rank + t) % n_ranks]) + row_off;
       for (int s = 0; s < n_splits; ++s) a += src[s * split_stride + j];
     }
     a *= logit_scale;
@@ -132,7 +138,8 @@ row_softmax_p2p_kernel(PeerPtrs partial, int n_ranks, int n_splits, int H, int C
   auto emit = [&](int j, float p) {                 // fp32 map row -> rank 0; 16-bit row -> every rank
     if (mdst && j < C) mdst[j] = p;
     if (j < ld_lp) {
-      for (int g = 0; g < n_ranks; ++g) {
+      for (int t = 0; t < n_ranks; ++t) {
+        const int g = (rank + t) % n_ranks;
         if constexpr (kLp == 1)
           reinterpret_cast<__nv_bfloat16*>(probs.p[g])[lp_off + j] = __float2bfloat16(p);
         else
@@ -159,7 +166,7 @@ constexpr int kP2pT = 8;   // C <= 512 * kP2pT
 
 template <int kLp>
 __global__ void __launch_bounds__(128)
-row_softmax_p2p_vec_kernel(PeerPtrs partial, int n_ranks, int n_splits, int H, int C, int i0, int rows_owned,
+row_softmax_p2p_vec_kernel(PeerPtrs partial, int n_ranks, int rank, int n_splits, int H, int C, int i0, int rows_owned,
                            const uint8_t* __restrict__ key_pad, float logit_scale, float* map_rank0, PeerPtrs probs,
                            int ld_lp) {
   __shared__ float red[8];
@@ -172,8 +179,8 @@ row_softmax_p2p_vec_kernel(PeerPtrs partial, int n_ranks, int n_splits, int H, i
   for (int k = 0; k < kP2pT; ++k)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[k][e] = 0.f;
-  for (int g = 0; g < n_ranks; ++g) {
-    const float* src = reinterpret_cast<const float*>(partial.p[g]) + row_off;
+  for (int t = 1; t <= n_ranks; ++t) {              // rotated: rank r pulls from r+1, r+2, ... (no source hot spot)
+    const float* src = reinterpret_cast<const float*>(partial.p[(rank + t) % n_ranks]) + row_off;
     for (int s = 0; s < n_splits; ++s) {
 #pragma unroll
       for (int k = 0; k < kP2pT; ++k) {
@@ -225,11 +232,11 @@ row_softmax_p2p_vec_kernel(PeerPtrs partial, int n_ranks, int n_splits, int H, i
       if (map_rank0) *reinterpret_cast<float4*>(map_rank0 + row_off + j) = p;
       const uint2 pk = kLp == 1 ? make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w))
                                 : make_uint2(pack_f16(p.x, p.y), pack_f16(p.z, p.w));
-      for (int g = 0; g < n_ranks; ++g)
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(probs.p[g]) + lp_off + j) = pk;
+      for (int t = 0; t < n_ranks; ++t)
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(probs.p[(rank + t) % n_ranks]) + lp_off + j) = pk;
     } else if (j < ld_lp) {                                           // zero the padding columns [C, ld_lp)
-      for (int g = 0; g < n_ranks; ++g)
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(probs.p[g]) + lp_off + j) = make_uint2(0u, 0u);
+      for (int t = 0; t < n_ranks; ++t)
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(probs.p[(rank + t) % n_ranks]) + lp_off + j) = make_uint2(0u, 0u);
     }
   }
 }
@@ -277,11 +284,12 @@ int rnamsm_layernorm_push(const float* x, const float* w, const float* b, void* 
   if (n_rows <= 0) return 0;
   const int blocks = (int)std::min<long long>((n_rows + kLnWarpsP - 1) / kLnWarpsP, 148LL * 32);
   cudaStream_t st = (cudaStream_t)stream;
+  const int c_shift = (int)(((long long)(r0 / (Rn > 0 ? Rn : 1)) * (C / n_ranks)) % C);   // = rank * Cn
   ProfScope prof(KC_LAYERNORM, st);
   if (y_dtype == RNAMSM_BF16)
-    layernorm_push_kernel<1><<<blocks, kLnWarpsP * 32, 0, st>>>(x, w, b, dst, Rn, C, C / n_ranks, R, r0, D, eps);
+    layernorm_push_kernel<1><<<blocks, kLnWarpsP * 32, 0, st>>>(x, w, b, dst, Rn, C, C / n_ranks, R, r0, D, eps, c_shift);
   else
-    layernorm_push_kernel<2><<<blocks, kLnWarpsP * 32, 0, st>>>(x, w, b, dst, Rn, C, C / n_ranks, R, r0, D, eps);
+    layernorm_push_kernel<2><<<blocks, kLnWarpsP * 32, 0, st>>>(x, w, b, dst, Rn, C, C / n_ranks, R, r0, D, eps, c_shift);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -315,19 +323,19 @@ int rnamsm_row_softmax_p2p(void* const* peer_partial, int n_ranks, int rank, int
   ProfScope prof(KC_ROW_SOFTMAX, st);
   if (C % 4 == 0 && C <= 512 * kP2pT && ld_lp % 4 == 0) {
     if (dtype == RNAMSM_BF16)
-      row_softmax_p2p_vec_kernel<1><<<(int)rows, 128, 0, st>>>(pp, n_ranks, n_splits, H, C, i0, Cq, key_pad, logit_scale,
+      row_softmax_p2p_vec_kernel<1><<<(int)rows, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, Cq, key_pad, logit_scale,
                                                             map_rank0, pr, ld_lp);
     else
-      row_softmax_p2p_vec_kernel<2><<<(int)rows, 128, 0, st>>>(pp, n_ranks, n_splits, H, C, i0, Cq, key_pad, logit_scale,
+      row_softmax_p2p_vec_kernel<2><<<(int)rows, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, Cq, key_pad, logit_scale,
                                                             map_rank0, pr, ld_lp);
     count_launch();
     RNAMSM_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
   if (dtype == RNAMSM_BF16)
-    row_softmax_p2p_kernel<1><<<blocks, 128, 0, st>>>(pp, n_ranks, n_splits, H, C, i0, i1, key_pad, logit_scale, map_rank0, pr, ld_lp);
+    row_softmax_p2p_kernel<1><<<blocks, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, i1, key_pad, logit_scale, map_rank0, pr, ld_lp);
   else
-    row_softmax_p2p_kernel<2><<<blocks, 128, 0, st>>>(pp, n_ranks, n_splits, H, C, i0, i1, key_pad, logit_scale, map_rank0, pr, ld_lp);
+    row_softmax_p2p_kernel<2><<<blocks, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, i1, key_pad, logit_scale, map_rank0, pr, ld_lp);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -74,6 +74,7 @@ struct GemmArgs {
   // m = r * Cn + c_local of this rank's column shard is reduce-added into row (r % Rn) * C + c0 + c_local
   // of the fp32 residual stream of rank r / Rn, through that rank's tensor map.
   int peer_n, peer_Rn, peer_Cn, peer_c0, peer_box_rows;
+  int m_tile_shift;      // DENSE: m-tile order rotated by this (per-rank) so ranks scatter to different owners at once
 };
 
 struct PeerMaps { CUtensorMap m[RNAMSM_MAX_PEERS]; };
@@ -89,7 +90,9 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile) {
   TileCoord t;
   if (kVariant == V_DENSE) {
     t.n0 = (tile % g.n_tiles) * BLOCK_N;
-    t.m0 = (tile / g.n_tiles) * PAIR_M;
+    int mt = tile / g.n_tiles + g.m_tile_shift;
+    if (mt >= g.m_tiles) mt -= g.m_tiles;
+    t.m0 = mt * PAIR_M;
     t.batch = 0; t.split = 0; t.kb_begin = 0; t.kb_count = g.k_blocks;
   } else if (kVariant == V_TIED) {
     t.n0 = (tile % g.n_tiles) * BLOCK_N;  tile /= g.n_tiles;
@@ -559,6 +562,7 @@ int launch_linear_16_scatter(const void* x, const void* W, const float* bias, in
   g.fp16 = fp16;
   g.epi_kind = as_delta16 ? RNAMSM_EPI_BIAS : RNAMSM_EPI_BIAS_RESIDUAL; g.bias = bias; g.q_scale = 1.f;
   g.peer_n = n_ranks; g.peer_Rn = Rn; g.peer_Cn = Cn; g.peer_c0 = c0; g.peer_box_rows = box_rows;
+  g.m_tile_shift = (int)(((long long)(c0 / Cn) * g.m_tiles) / n_ranks);   // rank * m_tiles / n: start at our own rows' owner
   return launch_variant<V_DENSE>(ta, tb, pm.m[0], g, KC_LINEAR_OUT, st, &pm);
 }
 
