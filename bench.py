@@ -43,7 +43,26 @@ WORKLOADS = {
     "cfg2": (512, 256, True, "cfg2 synthetic MSA depth 512 x L 256 (token grid 512x256), batch 1"),
     "cfg4": (4096, 128, False, "cfg4 synthetic deep MSA depth 4096 x L 128, embed_positions_msa=False"),
     "cfg5": (1024, 1024, True, "cfg5 synthetic long MSA depth 1024 x L 1024 token grid"),
+    # cfg3: 64 independent MSAs, depth 256, L ~ U{50..500} (seeded), farmed over the ranks longest-first
+    "cfg3": (256, None, True, "cfg3 batch of 64 synthetic MSAs, depth 256, L 50-500 (RNAcmap3-like), one B=1 forward each, "
+                              "longest-processing-time-first assignment over the ranks, no collective"),
 }
+
+
+def cfg3_lengths(n=64, seed=3):
+    import random
+    rng = random.Random(seed)
+    return [rng.randint(50, 500) + 1 for _ in range(n)]          # token columns C = L + 1 (BOS)
+
+
+def lpt_assign(costs, world):
+    """Longest-processing-time-first: job indices per rank."""
+    loads, jobs = [0.0] * world, [[] for _ in range(world)]
+    for i in sorted(range(len(costs)), key=lambda i: -costs[i]):
+        g = min(range(world), key=lambda r: loads[r])
+        loads[g] += costs[i]
+        jobs[g].append(i)
+    return jobs
 D, H, F, NL, V = 768, 12, 3072, 10, 12
 
 
@@ -145,6 +164,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     R, C, epm, desc = WORKLOADS[args.workload]
+    if C is None:                                        # cfg3: bounded sample = the median-length MSA of the batch
+        lens = cfg3_lengths()
+        C = sorted(lens)[len(lens) // 2]
     tokens = R * C
     times = []
     threads = os.cpu_count()
@@ -189,7 +211,15 @@ def run_ours(args):
     from oracle import msa_ref as O   # seeded weights / tokens recipe only (+ cpu_baseline leg)
 
     R, C, epm, desc = WORKLOADS[args.workload]
-    tokens_per_step = R * C
+    farm = C is None                                   # cfg3: a list of MSAs per rank instead of one shape
+    if farm:
+        lens = cfg3_lengths()
+        mine = lpt_assign([O.flops(R, c) for c in lens], world)[rank]
+        my_C = [lens[i] for i in mine]
+        C = max(lens)
+        tokens_per_step = R * sum(lens)                # whole job (all ranks)
+    else:
+        tokens_per_step = R * C
     vocab = pkg.Vocab(pkg.Alphabet())
     model = pkg.MSATransformer(vocab, num_layers=NL, embed_positions_msa=epm, precision=args.precision)
     model.load_state_dict(O.make_weights(42, embed_positions_msa=epm), strict=True)
@@ -208,15 +238,33 @@ def run_ours(args):
         tok_host = O.make_tokens(R, C, seed=100).pin_memory()      # the SAME MSA on every rank
         tok_dev = tok_host.cuda()
 
+    if farm:
+        farm_host = [O.make_tokens(R, c, seed=200 + i).pin_memory() for i, c in zip(mine, my_C)]
+        farm_dev = [t.cuda() for t in farm_host]
+
     def step_device():
         if shard:
             return sharded_forward(model, tok_dev, fused=args.fused)
+        if farm:
+            out = None
+            for t in farm_dev:
+                out = model(t, repr_layers=[NL], need_head_weights=True, want_logits=False)
+            return out
         return model(tok_dev, repr_layers=[NL], need_head_weights=True, want_logits=False)
 
     emb_host = torch.empty((C - 1, D), dtype=torch.float32).pin_memory()
     atp_host = torch.empty((NL * H, C - 1, C - 1), dtype=torch.float32).pin_memory()
 
     def step_e2e():
+        if farm:
+            for th in farm_host:
+                c = th.shape[-1]
+                out = model(th.cuda(non_blocking=True), repr_layers=[NL], need_head_weights=True, want_logits=False)
+                atp_host[:, :c - 1, :c - 1].copy_(out["row_attentions"][0, :, :, 1:, 1:].reshape(-1, c - 1, c - 1),
+                                                  non_blocking=True)
+                emb_host[:c - 1].copy_(out["representations"][NL][0, 0, 1:, :], non_blocking=True)
+            torch.cuda.synchronize()
+            return
         t = tok_host.cuda(non_blocking=True)
         if shard:
             out = sharded_forward(model, t, fused=args.fused)
@@ -272,11 +320,17 @@ def run_ours(args):
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
-        jobs = 1 if shard else world          # sharded: one MSA for the whole box; default: one MSA per rank
+        jobs = 1 if (shard or farm) else world   # sharded / cfg3: tokens_per_step already is the whole job
         value = jobs * tokens_per_step / (ms_per_step * 1e-3)
         e2e_value = jobs * tokens_per_step / (e2e_s / args.steps)
         peaks = measured_peaks()
-        fl = flops_breakdown(R, C)
+        if farm:                                        # this rank's MSAs
+            fl = {}
+            for c in my_C:
+                for k, v in flops_breakdown(R, c).items():
+                    fl[k] = fl.get(k, 0.0) + v
+        else:
+            fl = flops_breakdown(R, C)
         if shard:                                       # per-rank share of the one sharded MSA
             fl = {k: v / world for k, v in fl.items()}
         gemm_classes = ["linear_qkv", "linear_out_resid", "linear_fc1_gelu", "linear_fc2_resid"]
@@ -300,15 +354,22 @@ def run_ours(args):
             "share_of_kernel_time": round(gemm_ms / kernel_ms_total, 4) if kernel_ms_total else None,
             "traffic": None,
             "class_time_share": shares, "class_tflops": tflops,
-            "whole_forward_tflops_per_gpu": round(O.flops(R, C) / (world if shard else 1) * args.steps / (ms_total * 1e-3) / 1e12, 2),
+            "whole_forward_tflops_per_gpu": round((sum(O.flops(R, c) for c in my_C) if farm else O.flops(R, C) / (world if shard else 1))
+                                                  * args.steps / (ms_total * 1e-3) / 1e12, 2),
         }
         cpu = None
         if world == 1:                                  # contract: the CPU baseline is timed at N=1 only
-            t_emb, t_layer, threads = cpu_reference_sample(R, C, epm)
+            if farm:                                    # bounded sample: the median-length MSA of the batch
+                c_med = sorted(lens)[len(lens) // 2]
+                t_emb, t_layer, threads = cpu_reference_sample(R, c_med, epm)
+                tokens_per_step_cpu = R * c_med
+            else:
+                t_emb, t_layer, threads = cpu_reference_sample(R, C, epm)
+                tokens_per_step_cpu = tokens_per_step
             per_fwd = t_emb + NL * t_layer
-            cpu = {"value": tokens_per_step / per_fwd, "unit": "tokens/s", "cores": threads, "kind": "port",
+            cpu = {"value": tokens_per_step_cpu / per_fwd, "unit": "tokens/s", "cores": threads, "kind": "port",
                    "sample": f"embedding + ONE of {NL} AxialTransformerLayers of the oracle (fp32 torch CPU port of "
-                             f"modules.py:242-267) at the full {R}x{C} shape = {t_emb + t_layer:.1f} s, x{NL} layers"}
+                             f"modules.py:242-267) at the full {R}x{c_med if farm else C} shape = {t_emb + t_layer:.1f} s, x{NL} layers"}
         line = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -326,8 +387,9 @@ def run_ours(args):
                        "l2": "no explicit flush: per-step working set (>= 1.4 GB activations + 183 MB weights at "
                              "cfg2) exceeds the 126 MB L2"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": tok_host.numel() * 8,
-                    "d2h_bytes_per_step": atp_host.numel() * 4 + emb_host.numel() * 4,
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": (sum(t.numel() for t in farm_host) if farm else tok_host.numel()) * 8,
+                    "d2h_bytes_per_step": (sum(NL * H * (c - 1) ** 2 + (c - 1) * D for c in my_C) if farm
+                                           else atp_host.numel() + emb_host.numel()) * 4,
                     "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches),
             "roofline": roofline,
