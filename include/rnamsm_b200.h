@@ -135,6 +135,13 @@ int rnamsm_col_attn(const void* qkv, int R, int C, int H, int dtype, int qkv_col
 int rnamsm_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
                       void* stream);
 
+/* Contact head -- ContactPredictionHead.forward, modules.py:347-366 with
+ * utils/tensor.py:98-113: over the L x L block [start, start+L)^2 of each of the K = layers*heads maps
+ * (maps fp32 [K, C, C]; start = 1 strips BOS, model.py:412-414): symmetrize, average-product correction,
+ * then sigmoid(bias + sum_k w[k] * .) -> out fp32 [L, L].  workspace: K*L + K floats. */
+int rnamsm_contact_head(const float* maps, int K, int C, int start, int L, const float* w, const float* bias,
+                        float* out, float* workspace, void* stream);
+
 /* ---- whole-layer / whole-model drivers (same kernels, one call) ------------------------------ */
 
 typedef struct rnamsm_attn_weights {

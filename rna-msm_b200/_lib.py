@@ -59,6 +59,7 @@ SIGNATURES = {
     "rnamsm_row_attn_av": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "rnamsm_col_attn": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnamsm_vocab_proj": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "rnamsm_contact_head": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rnamsm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "rnamsm_layer_forward": (_i, [C.POINTER(LayerWeights), _i, _i, _i, _f, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "rnamsm_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),

@@ -36,7 +36,7 @@ static std::vector<ProfEvent> g_prof_events;
 static std::vector<cudaEvent_t> g_prof_pool;
 static const char* kClassNames[KC_COUNT] = {"embed_ln", "layernorm", "row_softmax", "vocab_proj", "linear_qkv",
                                             "linear_fc1_gelu", "linear_out_resid", "linear_fc2_resid",
-                                            "row_logits", "row_av", "col_attn"};
+                                            "row_logits", "row_av", "col_attn", "contact_head"};
 static cudaEvent_t prof_get_event() {
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
   cudaEvent_t e = nullptr;

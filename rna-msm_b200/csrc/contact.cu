@@ -1,0 +1,119 @@
+// Contact head on the device (SURVEY.md 8f "next" row 2): ContactPredictionHead.forward, modules.py:347-366,
+// with utils/tensor.py:98-113 (symmetrize, average-product correction) fused with the 120 -> 1 logistic
+// regression.  For every map k over the L x L block left after stripping BOS (/EOS):
+//     S_k = A_k + A_k^T,  a1_k[i] = sum_j S_k[i,j],  a12_k = sum_i a1_k[i],
+//     contacts[i,j] = sigmoid( b + sum_k w_k (S_k[i,j] - a1_k[i] a1_k[j] / a12_k) )
+// HBM-bound: the maps are read twice for the margins (rows + columns) and twice for the output
+// (tile + transposed tile); nothing of size [K, L, L] is written.  Deterministic (no atomics).
+#include "../../include/rnamsm_b200.h"
+#include "common.cuh"
+#include "launch.h"
+
+namespace rnamsm {
+
+// grid (ceil(L/32), K), block (32, 8): a1[k, i] for the 32 indices of the tile = row sum + column sum.
+__global__ void __launch_bounds__(256)
+contact_margins_kernel(const float* __restrict__ maps, int C, int start, int L, float* __restrict__ a1) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int k = blockIdx.y, i0 = blockIdx.x * 32;
+  const float* A = maps + (size_t)k * C * C + (size_t)start * C + start;   // the L x L block, row stride C
+  // column sums of columns i0 + tx: rows ty, ty + 8, ... (each warp reads 128 contiguous bytes per row)
+  float cs = 0.f;
+  if (i0 + tx < L)
+    for (int j = ty; j < L; j += 8) cs += A[(size_t)j * C + i0 + tx];
+  red[ty][tx] = cs;
+  __syncthreads();
+  // row sums of rows i0 + ty*4 + r: lanes stride over the columns
+  float rs[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty * 4 + r;
+    float s = 0.f;
+    if (i < L)
+      for (int j = tx; j < L; j += 32) s += A[(size_t)i * C + j];
+    rs[r] = warp_sum(s);
+  }
+  if (ty == 0 && i0 + tx < L) {
+    float c = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) c += red[y][tx];
+    red[0][tx] = c;
+  }
+  __syncthreads();
+  if (tx < 4) {
+    const int i = i0 + ty * 4 + tx;
+    if (i < L) a1[(size_t)k * L + i] = rs[tx] + red[0][ty * 4 + tx];
+  }
+}
+
+// one warp per map: a12[k] = sum_i a1[k, i]
+__global__ void __launch_bounds__(128)
+contact_total_kernel(const float* __restrict__ a1, int K, int L, float* __restrict__ a12) {
+  const int k = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int i = lane; i < L; i += 32) s += a1[(size_t)k * L + i];
+  s = warp_sum(s);
+  if (lane == 0) a12[k] = s;
+}
+
+// grid (ceil(L/32), ceil(L/32)), block (32, 8): thread (tx, ty) owns (i = i0 + ty + 8r, j = j0 + tx), r < 4.
+__global__ void __launch_bounds__(256)
+contact_out_kernel(const float* __restrict__ maps, int K, int C, int start, int L, const float* __restrict__ a1,
+                   const float* __restrict__ a12, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ out) {
+  __shared__ float T[32][33];
+  __shared__ float ai[32], aj[32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < K; ++k) {
+    const float* A = maps + (size_t)k * C * C + (size_t)start * C + start;
+    __syncthreads();                                   // previous iteration's smem fully consumed
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                      // transposed tile: rows j0.., columns i0..
+      const int jj = j0 + ty + 8 * r, ii = i0 + tx;
+      T[ty + 8 * r][tx] = (jj < L && ii < L) ? A[(size_t)jj * C + ii] : 0.f;
+    }
+    if (ty == 0) ai[tx] = (i0 + tx < L) ? a1[(size_t)k * L + i0 + tx] : 0.f;
+    if (ty == 1) aj[tx] = (j0 + tx < L) ? a1[(size_t)k * L + j0 + tx] : 0.f;
+    __syncthreads();
+    const float wk = w[k], inv = 1.f / a12[k];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + ty + 8 * r, j = j0 + tx;
+      if (i < L && j < L) {
+        const float s = A[(size_t)i * C + j] + T[tx][ty + 8 * r];             // A_ij + A_ji
+        acc[r] = fmaf(wk, s - ai[ty + 8 * r] * aj[tx] * inv, acc[r]);
+      }
+    }
+  }
+  const float b = bias ? bias[0] : 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty + 8 * r, j = j0 + tx;
+    if (i < L && j < L) out[(size_t)i * L + j] = 1.f / (1.f + __expf(-(acc[r] + b)));
+  }
+}
+
+}  // namespace rnamsm
+
+using namespace rnamsm;
+
+extern "C" int rnamsm_contact_head(const float* maps, int K, int C, int start, int L, const float* w, const float* bias,
+                                   float* out, float* workspace, void* stream) {
+  RNAMSM_REQUIRE(K > 0 && C > 0 && start >= 0 && L > 0 && start + L <= C, "contact_head: bad block start=%d L=%d of C=%d", start, L, C);
+  RNAMSM_REQUIRE(workspace != nullptr, "contact_head: workspace of (K*L + K) floats required");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* a1 = workspace;
+  float* a12 = workspace + (size_t)K * L;
+  const int tiles = ceil_div(L, 32);
+  ProfScope prof(KC_CONTACT, st);
+  contact_margins_kernel<<<dim3(tiles, K), dim3(32, 8), 0, st>>>(maps, C, start, L, a1);
+  contact_total_kernel<<<ceil_div(K, 4), 128, 0, st>>>(a1, K, L, a12);
+  contact_out_kernel<<<dim3(tiles, tiles), dim3(32, 8), 0, st>>>(maps, K, C, start, L, a1, a12, w, bias, out);
+  count_launch(3);
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -14,7 +14,7 @@ long long launch_count();
 // for the live roofline figure and the per-kernel time shares.  Off by default: zero overhead.
 enum KernelClass {
   KC_EMBED_LN = 0, KC_LAYERNORM, KC_ROW_SOFTMAX, KC_VOCAB_PROJ, KC_LINEAR_QKV, KC_LINEAR_FC1, KC_LINEAR_OUT,
-  KC_LINEAR_FC2, KC_ROW_LOGITS, KC_ROW_AV, KC_COL_ATTN, KC_COUNT
+  KC_LINEAR_FC2, KC_ROW_LOGITS, KC_ROW_AV, KC_COL_ATTN, KC_CONTACT, KC_COUNT
 };
 struct ProfScope {
   int cls;

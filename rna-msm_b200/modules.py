@@ -385,9 +385,9 @@ class RobertaLMHead(nn.Module):
 
 
 class ContactPredictionHead(nn.Module):
-    """Symmetrize + APC + logistic regression over the 120 maps (modules.py:322-366).  Outside the
-    kernel scope ('next'); kept as a few torch ops on the device so that
-    ``return_contacts=True`` / ``predict_contacts`` work and the state dict loads strictly."""
+    """Symmetrize + APC + logistic regression over the 120 maps (modules.py:322-366), on the device in
+    three small HBM-bound kernels (``rnamsm_contact_head``).  Keeps the
+    reference's parameter (``regression.{weight,bias}``) so the state dict loads strictly."""
 
     def __init__(self, in_features: int, prepend_bos: bool, append_eos: bool, bias=True, eos_idx: Optional[int] = None):
         super().__init__()
@@ -402,20 +402,24 @@ class ContactPredictionHead(nn.Module):
 
     @torch.no_grad()
     def forward(self, tokens, attentions):
+        L.require_cuda(attentions, "attentions")
         if self.append_eos:
+            # modules.py:349-353 zeroes the EOS row/column and drops the last position; the RNA alphabet
+            # never appends EOS (msm/data.py:166-172), so this branch only keeps other vocabularies working
             eos_mask = tokens.ne(self.eos_idx).to(attentions)
             eos_mask = eos_mask.unsqueeze(1) * eos_mask.unsqueeze(2)
             attentions = attentions * eos_mask[:, None, None, :, :]
-            attentions = attentions[..., :-1, :-1]
-        if self.prepend_bos:
-            attentions = attentions[..., 1:, 1:]
-        batch_size, layers, heads, seqlen, _ = attentions.size()
-        attentions = attentions.reshape(batch_size, layers * heads, seqlen, seqlen)
-        attentions = attentions.to(next(self.parameters()))
-        sym = attentions + attentions.transpose(-1, -2)
-        a1 = sym.sum(-1, keepdim=True)
-        a2 = sym.sum(-2, keepdim=True)
-        a12 = sym.sum((-1, -2), keepdim=True)
-        normalized = sym - a1 * a2 / a12
-        normalized = normalized.permute(0, 2, 3, 1)
-        return self.activation(self.regression(normalized).squeeze(3))
+        batch_size, layers, heads, Cc, _ = attentions.size()
+        start = 1 if self.prepend_bos else 0
+        seqlen = Cc - start - (1 if self.append_eos else 0)
+        K = layers * heads
+        maps = attentions.float().contiguous()
+        w = self.regression.weight.detach().float().reshape(-1).contiguous()
+        b = self.regression.bias.detach().float().contiguous() if self.regression.bias is not None else None
+        out = torch.empty((batch_size, seqlen, seqlen), dtype=torch.float32, device=maps.device)
+        ws = torch.empty(K * seqlen + K, dtype=torch.float32, device=maps.device)
+        with torch.cuda.device(maps.device):
+            for bi in range(batch_size):
+                L.check(L.lib.rnamsm_contact_head(L.ptr(maps[bi]), K, Cc, start, seqlen, L.ptr(w), L.ptr(b), L.ptr(out[bi]),
+                                                  L.ptr(ws), L.stream_ptr()), "contact_head")
+        return out

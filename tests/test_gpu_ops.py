@@ -226,3 +226,21 @@ def test_error_paths(L):
         L.check(L.lib.rnamsm_layernorm(L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), 0, 4, 100, 1e-5, 0, 0, L.stream_ptr()), "ln")
     with pytest.raises(RuntimeError, match="R=1"):
         L.check(L.lib.rnamsm_col_attn(L.ptr(x), 1, 4, 12, 0, 0, None, L.ptr(x), L.stream_ptr()), "col")
+
+
+# ------------------------------------------------------------------------------------------ contact head (8f row 2)
+@pytest.mark.parametrize("C,K", [(9, 24), (36, 120), (70, 120), (131, 120)])
+def test_contact_head_kernel(L, C, K):
+    """rnamsm_contact_head vs the oracle's symmetrize + APC + logistic regression (modules.py:347-366)."""
+    g = torch.Generator().manual_seed(5)
+    maps = torch.rand(1, K // 12, 12, C, C, generator=g).softmax(-1)
+    sd = {"contact_head.regression.weight": gen((1, K), 6), "contact_head.regression.bias": gen((1,), 7)}
+    ref = O.contact_head({k: v.double() for k, v in sd.items()}, None, maps.double())[0]
+    Ls = C - 1
+    md = maps[0].reshape(K, C, C).contiguous().cuda()
+    w, b = sd["contact_head.regression.weight"].reshape(-1).cuda(), sd["contact_head.regression.bias"].cuda()
+    out = torch.empty(Ls, Ls, device="cuda")
+    ws = torch.empty(K * Ls + K, device="cuda")
+    L.check(L.lib.rnamsm_contact_head(L.ptr(md), K, C, 1, Ls, L.ptr(w), L.ptr(b), L.ptr(out), L.ptr(ws), L.stream_ptr()))
+    assert rel(out, ref) < 1e-5
+    assert torch.equal(out, out.T) or rel(out, out.T) < 1e-6      # contacts are symmetric
