@@ -49,6 +49,21 @@ WORKLOADS = {
 }
 
 
+def total_flops(R, C):
+    """Algorithmic FLOPs of one forward: N [32 T D^2 + 4 T D (R + C)] + 2 T (D^2 + V D)."""
+    T = R * C
+    return NL * (32.0 * T * D * D + 4.0 * T * D * (R + C)) + 2.0 * T * (D * D + V * D)
+
+
+def synthetic_tokens(R, C, seed):
+    """Synthetic MSA: uniform over A,G,C,U,X,N,- (indices 4..10), column 0 = <cls>, no <pad>."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randint(4, 11, (1, R, C), generator=g, dtype=torch.int64)
+    t[:, :, 0] = 0
+    return t
+
+
 def cfg3_lengths(n=64, seed=3):
     import random
     rng = random.Random(seed)
@@ -208,23 +223,24 @@ def run_ours(args):
 
     import rnamsm_b200 as pkg
     from rnamsm_b200 import _lib
-    from oracle import msa_ref as O   # seeded weights / tokens recipe only (+ cpu_baseline leg)
+    # NB: the measured arm never touches oracle/: weights are the model's own random init (the reference
+    # recipe, model.py:89-101), tokens are generated here.  Only cpu_reference_sample() imports the oracle.
 
     R, C, epm, desc = WORKLOADS[args.workload]
     farm = C is None                                   # cfg3: a list of MSAs per rank instead of one shape
     if farm:
         lens = cfg3_lengths()
-        mine = lpt_assign([O.flops(R, c) for c in lens], world)[rank]
+        mine = lpt_assign([total_flops(R, c) for c in lens], world)[rank]
         my_C = [lens[i] for i in mine]
         C = max(lens)
         tokens_per_step = R * sum(lens)                # whole job (all ranks)
     else:
         tokens_per_step = R * C
     vocab = pkg.Vocab(pkg.Alphabet())
+    torch.manual_seed(42)                              # seed_everything(42), RNA_MSM_Inference.py:17
     model = pkg.MSATransformer(vocab, num_layers=NL, embed_positions_msa=epm, precision=args.precision)
-    model.load_state_dict(O.make_weights(42, embed_positions_msa=epm), strict=True)
     model = model.eval().cuda()
-    tok_host = O.make_tokens(R, C, seed=100 + rank).pin_memory()
+    tok_host = synthetic_tokens(R, C, seed=100 + rank).pin_memory()
     tok_dev = tok_host.cuda()
 
     def barrier():
@@ -235,11 +251,11 @@ def run_ours(args):
     shard = bool(args.shard) and world > 1
     if shard:
         from rnamsm_b200.sharded import sharded_forward
-        tok_host = O.make_tokens(R, C, seed=100).pin_memory()      # the SAME MSA on every rank
+        tok_host = synthetic_tokens(R, C, seed=100).pin_memory()   # the SAME MSA on every rank
         tok_dev = tok_host.cuda()
 
     if farm:
-        farm_host = [O.make_tokens(R, c, seed=200 + i).pin_memory() for i, c in zip(mine, my_C)]
+        farm_host = [synthetic_tokens(R, c, seed=200 + i).pin_memory() for i, c in zip(mine, my_C)]
         farm_dev = [t.cuda() for t in farm_host]
 
     def step_device():
@@ -354,7 +370,7 @@ def run_ours(args):
             "share_of_kernel_time": round(gemm_ms / kernel_ms_total, 4) if kernel_ms_total else None,
             "traffic": None,
             "class_time_share": shares, "class_tflops": tflops,
-            "whole_forward_tflops_per_gpu": round((sum(O.flops(R, c) for c in my_C) if farm else O.flops(R, C) / (world if shard else 1))
+            "whole_forward_tflops_per_gpu": round((sum(total_flops(R, c) for c in my_C) if farm else total_flops(R, C) / (world if shard else 1))
                                                   * args.steps / (ms_total * 1e-3) / 1e12, 2),
         }
         cpu = None
@@ -376,7 +392,7 @@ def run_ours(args):
             "scaling": "strong" if shard else "weak",
             "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "bf16_pure": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": desc, "R": R, "C": C, "tokens_per_step_per_gpu": tokens_per_step, "layers": NL,
-                       "embed_dim": D, "heads": H, "weights": "random-init (reference recipe, seed 42)",
+                       "embed_dim": D, "heads": H, "weights": "random-init (reference recipe model.py:89-101, seed 42)",
                        "precision": f"{args.precision}: 16-bit operands on tcgen05 (kind::f16), fp32 accumulate / residual "
                                     "stream / LayerNorm / softmax / exported maps" if args.precision != "fp32"
                                     else "fp32 FFMA parity path",
