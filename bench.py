@@ -49,6 +49,19 @@ WORKLOADS = {
 }
 
 
+def measured_traffic(workload, precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class, from the committed
+    ncu --set full capture of the same workload (profiles/r01c_traffic.json); None for other workloads."""
+    p = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("workload") == workload and d.get("precision") == precision:
+            return d["dense_gemm"]["dram_bytes_per_launch"], d["dense_gemm"]["algorithmic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None, None
+
+
 def total_flops(R, C):
     """Algorithmic FLOPs of one forward: N [32 T D^2 + 4 T D (R + C)] + 2 T (D^2 + V D)."""
     T = R * C
@@ -368,7 +381,9 @@ def run_ours(args):
             "flops_per_launch": gemm_flops_per_step / max(1, gemm_launches / args.steps),
             "avg_launch_ms": gemm_ms / max(1, gemm_launches), "launches": gemm_launches,
             "share_of_kernel_time": round(gemm_ms / kernel_ms_total, 4) if kernel_ms_total else None,
-            "traffic": None,
+            "traffic": measured_traffic(args.workload, args.precision)[0] if not (shard or farm) else None,
+            "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01c_traffic.json)",
+            "algorithmic_bytes_per_launch": measured_traffic(args.workload, args.precision)[1] if not (shard or farm) else None,
             "class_time_share": shares, "class_tflops": tflops,
             "whole_forward_tflops_per_gpu": round((sum(total_flops(R, c) for c in my_C) if farm else total_flops(R, C) / (world if shard else 1))
                                                   * args.steps / (ms_total * 1e-3) / 1e12, 2),
