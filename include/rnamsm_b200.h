@@ -142,6 +142,25 @@ int rnamsm_vocab_proj(const float* h, const float* E, const float* bias, long lo
 int rnamsm_contact_head(const float* maps, int K, int C, int start, int L, const float* w, const float* bias,
                         float* out, float* workspace, void* stream);
 
+/* ---- MSA ingest: the step in front of the hot path, on the device ---------------
+ * rnamsm_msa_clean: MSA.from_fasta's character rules (utils/align.py:311-313) as a per-row compaction.
+ *   raw = the record bodies back to back (newlines allowed), offsets [N+1] (int64) delimit record n;
+ *   chars_out uint8 [N, L]; *bad_row (device int) = 1 + index of a row whose cleaned length != L, else 0.
+ * rnamsm_msa_greedy_select: MSA.greedy_select (utils/align.py:128-148; sample_method "diversity-max" /
+ *   "diversity-min"): selected_out (device int32 [num]) = the sorted row indices, identical to the reference's
+ *   including how exact ties fall (its float64 mean is reproduced operation for operation: numpy's pairwise
+ *   sum over the picks, then / k, first index on equal values).  1 <= num <= min(N, 1024).
+ *   workspace: rnamsm_msa_greedy_workspace(N, num) bytes (N * (num-1) uint16 mismatch counts + scratch).
+ * rnamsm_msa_tokenize: Vocab.encode (utils/tokenization.py:107-129) of the selected rows (rows may be NULL
+ *   = all rows in order): tokens_out int64 [R, L+1], column 0 = bos, the input of rnamsm_msa_forward. */
+int rnamsm_msa_clean(const uint8_t* raw, const long long* offsets, int N, int L, uint8_t* chars_out, int* bad_row,
+                     void* stream);
+size_t rnamsm_msa_greedy_workspace(int N, int num);
+int rnamsm_msa_greedy_select(const uint8_t* chars, int N, int L, int num, int want_max, int* selected_out,
+                             void* workspace, void* stream);
+int rnamsm_msa_tokenize(const uint8_t* chars, int L, const int* rows, int R, const uint8_t* lut256, int bos,
+                        int64_t* tokens_out, void* stream);
+
 /* ---- whole-layer / whole-model drivers (same kernels, one call) ------------------------------ */
 
 typedef struct rnamsm_attn_weights {

@@ -11,8 +11,9 @@ from .modules import (AxialTransformerLayer, ColumnSelfAttention, ContactPredict
                       FeedForwardNetwork, LearnedPositionalEmbedding, NormalizedResidualBlock, RobertaLMHead,
                       RowSelfAttention)
 from .inference import extract_features, run_inference  # noqa: F401
+from .ingest import ingest_msa  # noqa: F401
 
 __all__ = ["MSATransformer", "AxialTransformerLayer", "RowSelfAttention", "ColumnSelfAttention",
            "FeedForwardNetwork", "NormalizedResidualBlock", "LearnedPositionalEmbedding", "RobertaLMHead",
            "ContactPredictionHead", "Alphabet", "Vocab", "read_msa", "tokenize_msa", "extract_features",
-           "run_inference"]
+           "run_inference", "ingest_msa"]

@@ -53,14 +53,15 @@ def build_model(model_path: Optional[str], device: str = "cuda", precision: str 
 
 @torch.no_grad()
 def run_inference(model: MSATransformer, vocab: Vocab, root_path: str, MSA_path: str, rna_ids, max_seqs_per_msa=512,
-                  max_seqlen=1024, verbose=True) -> str:
+                  max_seqlen=1024, verbose=True, sample_method: str = "first") -> str:
     save_feat_path = os.path.join(root_path, MSA_path)
     os.makedirs(save_feat_path, exist_ok=True)
     for rna_id in sorted(rna_ids):
         msa_file = os.path.join(root_path, MSA_path, rna_id + ".a2m_msa2")
-        tokens = tokenize_msa(msa_file, vocab, max_seqs_per_msa, max_seqlen).unsqueeze(0)
-        results = model(tokens.to(model.device), repr_layers=[model.num_layers], need_head_weights=True,
-                        want_logits=False)
+        # MSA ingest on the device (csrc/ingest.cu): cleaning, optional diversity sub-sampling, tokenisation
+        from .ingest import ingest_msa
+        tokens, _ = ingest_msa(msa_file, vocab, max_seqs_per_msa, max_seqlen, sample_method, device=str(model.device))
+        results = model(tokens.unsqueeze(0), repr_layers=[model.num_layers], need_head_weights=True, want_logits=False)
         emb, atp = extract_features(results, vocab, model.num_layers)
         np.save(os.path.join(save_feat_path, rna_id + "_atp.npy"), atp)
         np.save(os.path.join(save_feat_path, rna_id + "_emb.npy"), emb)
@@ -81,6 +82,9 @@ def main(argv=None):
     ap.add_argument("--max_seqlen", type=int, default=1024)
     ap.add_argument("--max_tokens", type=int, default=16384)
     ap.add_argument("--max_seqs_per_msa", type=int, default=512)
+    ap.add_argument("--sample_method", default="first", choices=["first", "diversity-max", "diversity-min"],
+                    help="the reference's default 'hhfilter' needs an external binary; 'first' keeps the first rows "
+                         "(what it does with hhfilter's surplus), 'diversity-*' is MSA.greedy_select on the GPU")
     ap.add_argument("--embed_dim", type=int, default=768)
     ap.add_argument("--num_attention_heads", type=int, default=12)
     ap.add_argument("--num_layers", type=int, default=10)
@@ -93,7 +97,8 @@ def main(argv=None):
     print(f"Inference on: {model.device}")
     with open(os.path.join(a.root_path, a.MSA_list)) as f:
         ids = f.read().splitlines()
-    run_inference(model, vocab, a.root_path, a.MSA_path, ids, a.max_seqs_per_msa, a.max_seqlen)
+    run_inference(model, vocab, a.root_path, a.MSA_path, ids, a.max_seqs_per_msa, a.max_seqlen,
+                  sample_method=a.sample_method)
 
 
 if __name__ == "__main__":
