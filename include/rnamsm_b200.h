@@ -142,6 +142,12 @@ int rnamsm_vocab_proj(const float* h, const float* E, const float* bias, long lo
 int rnamsm_contact_head(const float* maps, int K, int C, int start, int L, const float* w, const float* bias,
                         float* out, float* workspace, void* stream);
 
+/* SS-predictor input packing: _downstream_tasks/SS/code/pre_processing/data_processing.py:32-48
+ * + data_fomat.py:38-59 from the device-resident maps: out fp32 [8 + K, L, L] (= x[0] of the [1,128,L,L] input):
+ * channels 0-3 one-hot of seq[i] over A,C,G,U, 4-7 one-hot of seq[j], 8.. = map k over the block
+ * [start, start+L)^2.  seq_codes uint8 [L]: 0..3 = A,C,G,U, anything else = unknown (all-zero one-hot). */
+int rnamsm_ss_pack(const float* maps, int K, int C, int start, int L, const uint8_t* seq_codes, float* out, void* stream);
+
 /* ---- MSA ingest: the step in front of the hot path, on the device ---------------
  * rnamsm_msa_clean: MSA.from_fasta's character rules (utils/align.py:311-313) as a per-row compaction.
  *   raw = the record bodies back to back (newlines allowed), offsets [N+1] (int64) delimit record n;

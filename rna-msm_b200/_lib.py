@@ -63,6 +63,7 @@ SIGNATURES = {
     "rnamsm_msa_greedy_workspace": (_sz, [_i, _i]),
     "rnamsm_msa_greedy_select": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnamsm_msa_tokenize": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "rnamsm_ss_pack": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnamsm_contact_head": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rnamsm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "rnamsm_layer_forward": (_i, [C.POINTER(LayerWeights), _i, _i, _i, _f, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -117,3 +117,37 @@ extern "C" int rnamsm_contact_head(const float* maps, int K, int C, int start, i
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// SS-predictor input packing: what _downstream_tasks/SS builds on the CPU from the saved
+// *_atp.npy -- DataProcess.feature_load (code/pre_processing/data_processing.py:32-48: outer concatenation of the
+// ACGU one-hot [L,L,8] + maps transposed to [L,L,120]) followed by format_input_shape (data_fomat.py:38-59:
+// -> [1,128,L,L] float) -- straight from the device-resident maps: channel c < 4: onehot(seq[i])[c];
+// 4 <= c < 8: onehot(seq[j])[c-4]; c >= 8: map c-8 over the BOS-stripped block.  Pure HBM copy/gather.
+// ---------------------------------------------------------------------------------------------------------
+namespace rnamsm {
+__global__ void __launch_bounds__(256)
+ss_pack_kernel(const float* __restrict__ maps, int K, int C, int start, int L, const uint8_t* __restrict__ codes,
+               float* __restrict__ out) {
+  const int ch = blockIdx.z, i = blockIdx.y;
+  float* dst = out + ((size_t)ch * L + i) * L;
+  if (ch < 8) {
+    const int ci = codes[i];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x)
+      dst[j] = (ch < 4) ? (ci == ch ? 1.f : 0.f) : (codes[j] == ch - 4 ? 1.f : 0.f);
+  } else {
+    const float* src = maps + (size_t)(ch - 8) * C * C + (size_t)(start + i) * C + start;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x) dst[j] = src[j];
+  }
+}
+}  // namespace rnamsm
+
+extern "C" int rnamsm_ss_pack(const float* maps, int K, int C, int start, int L, const uint8_t* seq_codes, float* out,
+                              void* stream) {
+  RNAMSM_REQUIRE(K > 0 && L > 0 && start >= 0 && start + L <= C && L <= 65535 && K + 8 <= 65535, "ss_pack: bad shape");
+  dim3 grid(rnamsm::ceil_div(L, 256), L, K + 8);
+  rnamsm::ss_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(maps, K, C, start, L, seq_codes, out);
+  rnamsm::count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

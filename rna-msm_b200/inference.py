@@ -35,6 +35,27 @@ def extract_features(results: Dict[str, object], vocab: Vocab, num_layers: int) 
     return emb, atp
 
 
+@torch.no_grad()
+def pack_ss_input(row_attentions: torch.Tensor, sequence: str, prepend_bos: bool = True) -> torch.Tensor:
+    """The ``[1, 128, L, L]`` input of the downstream SS predictor (``_downstream_tasks/SS``:
+    ``DataProcess.feature_load`` + ``format_input_shape``) built on the device from ``row_attentions
+    [1, N, H, C, C]`` -- no ``*_atp.npy`` round trip, no O(L^2) Python loop (``outer_concatenation``)."""
+    from . import _lib as L
+    L.require_cuda(row_attentions, "row_attentions")
+    _, N, H, Cc, _ = row_attentions.shape
+    start = int(prepend_bos)
+    Ls = Cc - start
+    if len(sequence) != Ls:
+        raise ValueError(f"sequence length {len(sequence)} != map size {Ls}")
+    codes = torch.tensor([{"A": 0, "C": 1, "G": 2, "U": 3}.get(ch, 255) for ch in sequence], dtype=torch.uint8,
+                         device=row_attentions.device)
+    maps = row_attentions[0].float().contiguous()
+    out = torch.empty((1, 8 + N * H, Ls, Ls), dtype=torch.float32, device=maps.device)
+    with torch.cuda.device(maps.device):
+        L.check(L.lib.rnamsm_ss_pack(L.ptr(maps), N * H, Cc, start, Ls, L.ptr(codes), L.ptr(out), L.stream_ptr()), "ss_pack")
+    return out
+
+
 def build_model(model_path: Optional[str], device: str = "cuda", precision: str = "fp16", embed_dim: int = 768,
                 num_attention_heads: int = 12, num_layers: int = 10, embed_positions_msa: bool = True,
                 max_tokens: int = 16384, max_seqlen: int = 1024, seed: int = 42) -> Tuple[MSATransformer, Vocab]:

@@ -244,3 +244,18 @@ def test_contact_head_kernel(L, C, K):
     L.check(L.lib.rnamsm_contact_head(L.ptr(md), K, C, 1, Ls, L.ptr(w), L.ptr(b), L.ptr(out), L.ptr(ws), L.stream_ptr()))
     assert rel(out, ref) < 1e-5
     assert torch.equal(out, out.T) or rel(out, out.T) < 1e-6      # contacts are symmetric
+
+
+# ------------------------------------------------------------------------------------------ SS input packing (8f row 3)
+def test_ss_input_packing_matches_reference(golden_dir):
+    """pack_ss_input vs the [1,128,L,L] tensor the reference's own SS pre-processing builds (oracle/gen_golden_ss.py)."""
+    import os
+    import rnamsm_b200 as pkg
+    g = np.load(os.path.join(golden_dir, "ss_pack.npz"))
+    seq, atp, want = str(g["seq"]), g["atp"], g["x"]
+    Ls = len(seq)
+    ra = torch.zeros(1, 10, 12, Ls + 1, Ls + 1)
+    ra[0, :, :, 1:, 1:] = torch.from_numpy(atp).view(10, 12, Ls, Ls)       # maps with the BOS row / column back in
+    x = pkg.pack_ss_input(ra.cuda(), seq)
+    assert tuple(x.shape) == want.shape == (1, 128, Ls, Ls) and x.dtype == torch.float32
+    assert torch.equal(x.cpu(), torch.from_numpy(want))                    # bit-exact: copies and 0/1
