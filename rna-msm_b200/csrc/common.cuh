@@ -419,6 +419,12 @@ __device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
   return d;
 }
 
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ---- misc math -----------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

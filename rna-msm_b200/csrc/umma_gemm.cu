@@ -129,6 +129,29 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x >= 0.f ? x - h : h;
 }
 
+// Two erf-GELUs at once on packed fp32 pairs (FFMA2 / FMUL2 / FADD2): gelu(x) = 0.5 (x + |x| (1 - erfc(|x|/sqrt2))),
+// same A&S 7.1.28 erfc as gelu_fast.  ~19 issue slots per pair instead of ~36: the fc1 epilogue is issue-bound.
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const uint64_t x = f32x2_pack(x0, x1);
+  const uint64_t ax = x & 0x7fffffff7fffffffull;                              // |x|
+  const uint64_t z = f32x2_mul(ax, f32x2_pack(0.70710678118654752440f, 0.70710678118654752440f));
+  uint64_t p = f32x2_fma(z, f32x2_pack(0.0000430638f, 0.0000430638f), f32x2_pack(0.0002765672f, 0.0002765672f));
+  p = f32x2_fma(p, z, f32x2_pack(0.0001520143f, 0.0001520143f));
+  p = f32x2_fma(p, z, f32x2_pack(0.0092705272f, 0.0092705272f));
+  p = f32x2_fma(p, z, f32x2_pack(0.0422820123f, 0.0422820123f));
+  p = f32x2_fma(p, z, f32x2_pack(0.0705230784f, 0.0705230784f));
+  p = f32x2_fma(p, z, f32x2_pack(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  f32x2_unpack(p, p0, p1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+  uint64_t r = f32x2_pack(r0, r1);
+  r = f32x2_mul(r, r); r = f32x2_mul(r, r); r = f32x2_mul(r, r); r = f32x2_mul(r, r);   // erfc(z)
+  const uint64_t t = f32x2_fma(r, f32x2_pack(-1.0f, -1.0f), f32x2_pack(1.0f, 1.0f));  // 1 - erfc
+  const uint64_t u = f32x2_fma(ax, t, x);                                              // x + |x| (1 - erfc)
+  f32x2_unpack(f32x2_mul(u, f32x2_pack(0.5f, 0.5f)), x0, x1);
+}
+
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
   uint32_t r;
   if (fp16)
@@ -369,8 +392,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             __uint_as_float(v0[k + 2]) + b0.z, __uint_as_float(v0[k + 3]) + b0.w,
                             __uint_as_float(v1[k]) + b1.x, __uint_as_float(v1[k + 1]) + b1.y,
                             __uint_as_float(v1[k + 2]) + b1.z, __uint_as_float(v1[k + 3]) + b1.w};
+              if (gelu) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = gelu ? gelu_fast(a[e]) : a[e] * s;
+                for (int e = 0; e < 8; e += 2) gelu_fast2(a[e], a[e + 1]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] *= s;
+              }
               w[k / 2] = pack16(a[0], a[1], g.fp16);
               w[k / 2 + 1] = pack16(a[2], a[3], g.fp16);
               w[16 + k / 2] = pack16(a[4], a[5], g.fp16);

@@ -36,6 +36,61 @@ def extract_features(results: Dict[str, object], vocab: Vocab, num_layers: int) 
 
 
 @torch.no_grad()
+def extract_features_streamed(model: MSATransformer, tokens: torch.Tensor, atp_host: torch.Tensor,
+                              emb_host: torch.Tensor) -> None:
+    """``RNA_MSM_Inference.py:147-166`` for one MSA with the device->host copies overlapped with compute:
+    the forward runs layer by layer (``rnamsm_layer_forward``) and every layer's 12 maps start their copy into
+    the pinned ``atp_host [(N*H), L, L]`` on a side stream while the next layer computes; ``emb_host [L, D]``
+    follows the final LayerNorm.  ``tokens``: ``[1, R, C]`` int64, pinned host or device.  Returns when both
+    host buffers are complete."""
+    import ctypes as C
+    from . import _lib as L
+    dev = model.device
+    vocab = model.vocab
+    assert tokens.ndim == 3 and tokens.shape[0] == 1
+    _, R, Cc = tokens.shape
+    D, H, N = model.embed_dim, model.num_attention_heads, model.num_layers
+    if model.msa_position_embedding is not None and R > 1024:
+        raise RuntimeError("Using model with MSA position embedding trained on maximum MSA depth of 1024, "
+                           f"but received {R} alignments.")
+    start = int(vocab.prepend_bos)
+    Ls = Cc - start - int(vocab.append_eos)
+    with torch.cuda.device(dev):
+        code = model._code
+        main = torch.cuda.current_stream()
+        side = getattr(model, "_copy_stream", None)
+        if side is None:
+            side = model._copy_stream = torch.cuda.Stream()
+        tok = tokens.to(dev, non_blocking=True).long().contiguous()
+        has_pad = bool(tok.eq(vocab.pad_idx).any())
+        x = torch.empty((R * Cc, D), dtype=torch.float32, device=dev)
+        pad = torch.empty(R * Cc, dtype=torch.uint8, device=dev)
+        maps = torch.empty((N, H, Cc, Cc), dtype=torch.float32, device=dev)
+        m = model.c_weights(code)
+        nbytes = L.lib.rnamsm_workspace_bytes(R, Cc, D, H, 4 * D, code)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        st = L.stream_ptr()
+        L.check(L.lib.rnamsm_embed_layernorm(L.ptr(tok[0]), R, Cc, m.tok_emb, m.vocab, m.pos_emb, m.n_pos, m.row_pos,
+                                             m.ln_before_w, m.ln_before_b, D, m.pad_idx, m.ln_eps, L.ptr(x), L.ptr(pad), st),
+                "embed_layernorm")
+        for l in range(N):
+            L.check(L.lib.rnamsm_layer_forward(C.byref(m.layers[l]), D, H, 4 * D, m.ln_eps, L.ptr(x), R, Cc,
+                                               L.ptr(pad) if has_pad else None, code, L.ptr(maps[l]), L.ptr(ws), nbytes, st),
+                    "layer_forward")
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                atp_host[l * H:(l + 1) * H].copy_(maps[l, :, start:start + Ls, start:start + Ls], non_blocking=True)
+        L.check(L.lib.rnamsm_layernorm(L.ptr(x), m.ln_after_w, m.ln_after_b, L.ptr(x), L.F32, R * Cc, D, m.ln_eps, 0, 0, st),
+                "layernorm")
+        emb_host.copy_(x.view(R, Cc, D)[0, start:start + Ls], non_blocking=True)
+        maps.record_stream(side)
+        side.synchronize()
+        main.synchronize()
+
+
+@torch.no_grad()
 def pack_ss_input(row_attentions: torch.Tensor, sequence: str, prepend_bos: bool = True) -> torch.Tensor:
     """The ``[1, 128, L, L]`` input of the downstream SS predictor (``_downstream_tasks/SS``:
     ``DataProcess.feature_load`` + ``format_input_shape``) built on the device from ``row_attentions

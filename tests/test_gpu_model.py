@@ -217,3 +217,16 @@ def test_contacts_and_api_surface(pkg):
     model.train()
     with pytest.raises(RuntimeError, match="eval"):
         model(tokens.cuda())
+
+
+@pytest.mark.parametrize("pads", [0, 2])
+def test_streamed_extraction_equals_forward(pkg, pads):
+    """extract_features_streamed (layer-by-layer, D2H overlapped) == forward + extract_features, bit for bit."""
+    model, _ = build(pkg, 4, 3, 2.0, "fp16")
+    tokens = O.make_tokens(33, 41, 5, pad_cols=pads)
+    out = model(tokens.cuda(), repr_layers=[3], need_head_weights=True, want_logits=False)
+    emb, atp = pkg.extract_features(out, model.vocab, 3)
+    atp_h = torch.empty((3 * 12, 40, 40), dtype=torch.float32).pin_memory()
+    emb_h = torch.empty((40, 768), dtype=torch.float32).pin_memory()
+    pkg.extract_features_streamed(model, tokens.pin_memory(), atp_h, emb_h)
+    assert np.array_equal(atp_h.numpy(), atp) and np.array_equal(emb_h.numpy(), emb)
