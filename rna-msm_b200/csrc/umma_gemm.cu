@@ -85,17 +85,17 @@ struct TileCoord {
   int kb_begin, kb_count;
 };
 
-template <int kVariant>
+template <int kVariant, int kBN>
 __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile) {
   TileCoord t;
   if (kVariant == V_DENSE) {
-    t.n0 = (tile % g.n_tiles) * BLOCK_N;
+    t.n0 = (tile % g.n_tiles) * kBN;
     int mt = tile / g.n_tiles + g.m_tile_shift;
     if (mt >= g.m_tiles) mt -= g.m_tiles;
     t.m0 = mt * PAIR_M;
     t.batch = 0; t.split = 0; t.kb_begin = 0; t.kb_count = g.k_blocks;
   } else if (kVariant == V_TIED) {
-    t.n0 = (tile % g.n_tiles) * BLOCK_N;  tile /= g.n_tiles;
+    t.n0 = (tile % g.n_tiles) * kBN;  tile /= g.n_tiles;
     t.m0 = (tile % g.m_tiles) * PAIR_M;   tile /= g.m_tiles;
     t.split = tile % g.splits;
     t.batch = tile / g.splits;
@@ -170,16 +170,21 @@ __device__ __forceinline__ void stage_row(uint8_t* buf, int lane, const uint32_t
     *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
 
-template <int kVariant>
+// kBN = accumulator columns of the pair tile (256; 128 / 64 for the tied logits of short alignments, where a
+// 256-wide tile would be mostly padding): each CTA stages kBN / 2 rows of B, TMEM holds 2 x kBN columns.
+template <int kVariant, int kBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g,
                  const __grid_constant__ PeerMaps peers) {
+  constexpr int BN = kBN, HN = kBN / 2;
+  constexpr int STG = A_BYTES + HN * BLOCK_K * 2;        // bytes per CTA per k-block
+  constexpr int TMC = 2 * kBN;                           // TMEM columns (power of two >= 32)
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment (descriptor base_offset = 0).  The dynamic smem
   // window starts at the same offset in both CTAs, so the carve-up below is identical in the pair.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* epi_smem = smem + kStages * STAGE_BYTES;
+  uint8_t* epi_smem = smem + kStages * STG;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * EPI_BUF_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
@@ -210,7 +215,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc2(tmem_ptr, kTmemCols);
+    tmem_alloc2(tmem_ptr, TMC);
     tmem_relinquish2();
   }
   tc_fence_before();
@@ -224,20 +229,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        const TileCoord t = decode_tile<kVariant>(g, tile);
+        const TileCoord t = decode_tile<kVariant, kBN>(g, tile);
         for (int kb = 0; kb < t.kb_count; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sa = smem + stage * STG;
           uint8_t* sb = sa + A_BYTES;
           const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's full barrier
-          mbar_expect_tx_cluster(bar, STAGE_BYTES);
+          mbar_expect_tx_cluster(bar, STG);
           if (kVariant == V_DENSE) {
             tma_load_3d_2sm(sa, &tmap_a, bar, kb * BLOCK_K, t.m0 + cta_rank * BLOCK_M, 0);
-            tma_load_3d_2sm(sb, &tmap_b, bar, kb * BLOCK_K, t.n0 + cta_rank * HALF_N, 0);
+            tma_load_3d_2sm(sb, &tmap_b, bar, kb * BLOCK_K, t.n0 + cta_rank * HN, 0);
           } else if (kVariant == V_TIED) {
             const int r = t.kb_begin + kb;
             tma_load_3d_2sm(sa, &tmap_a, bar, t.batch * 64, t.m0 + cta_rank * BLOCK_M, r);
-            tma_load_3d_2sm(sb, &tmap_b, bar, (g.H + t.batch) * 64, t.n0 + cta_rank * HALF_N, r);
+            tma_load_3d_2sm(sb, &tmap_b, bar, (g.H + t.batch) * 64, t.n0 + cta_rank * HN, r);
           } else {
             tma_load_3d_2sm(sa, &tmap_a, bar, kb * BLOCK_K, t.m0 + cta_rank * BLOCK_M, t.batch);
             tma_load_3d_2sm(sb, &tmap_b, bar, (2 * g.H + t.batch) * 64, kb * BLOCK_K, t.n0 + cta_rank * 2);
@@ -249,18 +254,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA) =====================
     if (leader && elect_one()) {
-      const uint32_t idesc = make_idesc_16(PAIR_M, BLOCK_N, g.fp16, 0, kVariant == V_AV ? 1 : 0);
+      const uint32_t idesc = make_idesc_16(PAIR_M, BN, g.fp16, 0, kVariant == V_AV ? 1 : 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        const TileCoord t = decode_tile<kVariant>(g, tile);
+        const TileCoord t = decode_tile<kVariant, kBN>(g, tile);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < t.kb_count; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(smem + stage * STG);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -290,10 +295,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-      const TileCoord t = decode_tile<kVariant>(g, tile);
+      const TileCoord t = decode_tile<kVariant, kBN>(g, tile);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BLOCK_N + half * HALF_N + ((uint32_t)(quad * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * BN + half * HN + ((uint32_t)(quad * 32) << 16);
       const int row0 = t.m0 + cta_rank * BLOCK_M + quad * 32;   // first logical row of this warp's box
       auto release_acc = [&]() {                     // every tcgen05.ld of this tile has completed
         tc_fence_before();
@@ -305,12 +310,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // fp32 partial logits, direct stores (C need not be a multiple of 4)
         const int i = row0 + lane;
 #pragma unroll 1
-        for (int c = 0; c < HALF_N / 32; ++c) {
+        for (int c = 0; c < HN / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (c == HALF_N / 32 - 1) release_acc();
-          const int j0 = t.n0 + half * HALF_N + c * 32;
+          if (c == HN / 32 - 1) release_acc();
+          const int j0 = t.n0 + half * HN + c * 32;
           if (i >= g.C || j0 >= g.C) continue;
           float* dst = reinterpret_cast<float*>(g.out) + (((size_t)t.split * g.H + t.batch) * g.C + i) * g.C + j0;
           if ((g.C & 3) == 0 && j0 + 32 <= g.C) {
@@ -327,12 +332,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       } else if (kVariant == V_DENSE && g.epi_kind == RNAMSM_EPI_BIAS_RESIDUAL) {
         // out(fp32) += acc + bias: 32-column boxes, TMA reduce-add into the residual stream
 #pragma unroll 1
-        for (int c = 0; c < HALF_N / 32; ++c) {
+        for (int c = 0; c < HN / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (c == HALF_N / 32 - 1) release_acc();
-          const int n = t.n0 + half * HALF_N + c * 32;
+          if (c == HN / 32 - 1) release_acc();
+          const int n = t.n0 + half * HN + c * 32;
           if (n >= g.N || row0 >= g.M) continue;
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
@@ -367,16 +372,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       } else {
         // 16-bit outputs: 64-column boxes (128 B rows), TMA store
 #pragma unroll 1
-        for (int c = 0; c < HALF_N / 64; ++c) {
+        for (int c = 0; c < HN / 64; ++c) {
           uint32_t v0[32], v1[32];
           tmem_ld_32x32(taddr + c * 64, v0);
           tmem_ld_32x32(taddr + c * 64 + 32, v1);
           tmem_ld_wait();
-          if (c == HALF_N / 64 - 1) release_acc();
+          if (c == HN / 64 - 1) release_acc();
           uint32_t w[32];
           int c0, c1, c2;
           if (kVariant == V_DENSE) {
-            const int n = t.n0 + half * HALF_N + c * 64;
+            const int n = t.n0 + half * HN + c * 64;
             if (n >= g.N || row0 >= g.M) continue;
             float s = 1.f;
             if (g.epi_kind == RNAMSM_EPI_BIAS && n < g.q_cols) {   // q_cols is a multiple of 64
@@ -446,7 +451,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   cluster_sync();   // the peer's smem / barriers stay valid until both CTAs are done
-  if (warp == 2) tmem_dealloc2(tmem_base, kTmemCols);
+  if (warp == 2) tmem_dealloc2(tmem_base, TMC);
 }
 
 int num_sms() {
@@ -465,12 +470,12 @@ int num_sms() {
 // even number of usable SMs, so this can be below num_sms() / 2.
 int g_max_pairs = 0;
 
-template <int kVariant>
+template <int kVariant, int kBN = BLOCK_N>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g,
                    int prof_class, cudaStream_t st, const PeerMaps* peers = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
-    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes));
     attr_set = true;
   }
@@ -485,7 +490,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, umma_gemm_kernel<kVariant>, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, umma_gemm_kernel<kVariant, kBN>, &cfg);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
     const char* env = getenv("RNAMSM_GEMM_PAIRS");
     if (env && atoi(env) > 0) n = atoi(env);
@@ -496,7 +501,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int pairs = (int)std::min<long long>(total, g_max_pairs);
   ProfScope prof(prof_class, st);
   static const PeerMaps no_peers{};
-  umma_gemm_kernel<kVariant><<<2 * pairs, kThreads, kSmemBytes, st>>>(ta, tb, to, g, peers ? *peers : no_peers);
+  umma_gemm_kernel<kVariant, kBN><<<2 * pairs, kThreads, kSmemBytes, st>>>(ta, tb, to, g, peers ? *peers : no_peers);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -596,8 +601,10 @@ int launch_linear_16_scatter(const void* x, const void* W, const float* bias, in
 
 int gemm_max_pairs() { return g_max_pairs; }
 
+static inline int tied_tile_n(int C) { return C <= 64 ? 64 : (C <= 128 ? 128 : BLOCK_N); }
+
 int row_logits_splits_16(int R, int C, int H) {
-  const long long tiles = (long long)H * ceil_div(C, PAIR_M) * ceil_div(C, BLOCK_N);
+  const long long tiles = (long long)H * ceil_div(C, PAIR_M) * ceil_div(C, tied_tile_n(C));
   const int pairs = g_max_pairs > 0 ? g_max_pairs : num_sms() / 2;
   // smallest split count whose tile total fills the 74 CTA pairs in whole waves as evenly as possible
   int want = (int)std::max<long long>(1, (pairs + tiles - 1) / tiles);
@@ -626,18 +633,21 @@ int launch_row_logits_16(const void* qkv, int R, int C, int H, int fp16, float* 
   CUtensorMap ta, tb;
   uint64_t dims[3] = {(uint64_t)ld, (uint64_t)C, (uint64_t)R};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)C * ld * 2};
+  const int bn = tied_tile_n(C);
   uint32_t box_a[3] = {BLOCK_K, BLOCK_M, 1};
-  uint32_t box_b[3] = {BLOCK_K, HALF_N, 1};
+  uint32_t box_b[3] = {BLOCK_K, (uint32_t)(bn / 2), 1};
   if (encode_tmap(&ta, in_dt, qkv, 3, dims, strides, box_a)) return 3;
   if (encode_tmap(&tb, in_dt, qkv, 3, dims, strides, box_b)) return 3;
   GemmArgs g{};
   g.m_tiles = ceil_div(C, PAIR_M);
-  g.n_tiles = ceil_div(C, BLOCK_N);
+  g.n_tiles = ceil_div(C, bn);
   g.batches = H; g.splits = n_splits;
   g.rows_per_split = rps;
   g.R = R; g.C = C; g.H = H; g.M = C; g.N = C;
   g.fp16 = fp16;
   g.out = partial;
+  if (bn == 64) return launch_variant<V_TIED, 64>(ta, tb, ta, g, KC_ROW_LOGITS, st);
+  if (bn == 128) return launch_variant<V_TIED, 128>(ta, tb, ta, g, KC_ROW_LOGITS, st);
   return launch_variant<V_TIED>(ta, tb, ta, g, KC_ROW_LOGITS, st);
 }
 
