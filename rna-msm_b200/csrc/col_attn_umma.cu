@@ -1,4 +1,5 @@
-// K7, bf16 path: flash-style column attention on tcgen05 (modules.py:896-923).
+// K7, 16-bit path, shallow MSAs (R <= 128): flash-style column attention on tcgen05 (modules.py:896-923).
+// Deeper MSAs run the persistent warp-specialised kernel in col_attn_ws.cu.
 //
 // For every alignment column c and head h the MSA depth R is the sequence axis:
 //   ctx[i,c,h,:] = sum_j softmax_j(q[i,c,h,:] . k[j,c,h,:]) v[j,c,h,:]          (q pre-scaled by 64^-0.5)
@@ -93,7 +94,7 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + b * KV_BYTES);
 #pragma unroll
     for (int k = 0; k < HD / 16; ++k)
-      umma_bf16(tmem_S, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024),
+      umma_16(tmem_S, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024),
                 idesc_s, (uint32_t)(k != 0));
     umma_commit(s_ready);
   };
@@ -102,7 +103,7 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t pa = smem_u32(sP), va = smem_u32(sV + b * KV_BYTES);
 #pragma unroll
     for (int k = 0; k < BKV / 16; ++k)
-      umma_bf16(tmem_O, make_smem_desc_sw128(pa + k * 32, 16, 1024),
+      umma_16(tmem_O, make_smem_desc_sw128(pa + k * 32, 16, 1024),
                 make_smem_desc_sw128(va + k * 2048, 8192, 1024), idesc_o, (uint32_t)(k != 0));
     umma_commit(o_ready);
   };

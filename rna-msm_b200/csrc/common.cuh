@@ -150,12 +150,6 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -181,18 +175,6 @@ __device__ __forceinline__ void tc_fence_before() {
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 inputs, fp32 accumulate.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
@@ -287,29 +269,6 @@ __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, ui
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("rnamsm: cluster mbarrier wait timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x,
-             threadIdx.x, (void*)bar, parity);
-      __trap();
-    }
-  }
-}
 // TMA load issued by either CTA of a pair: data lands in the issuing CTA's smem, the byte count is
 // signalled on the mbarrier at `bar_cluster_addr` (the leader CTA's barrier).
 __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
@@ -384,15 +343,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
-//   [4,6) D fmt (1=f32)  [7,10) A fmt (1=bf16)  [10,13) B fmt (1=bf16)
-//   [15] A major (0=K,1=MN)  [16] B major  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// kind::f16 with f16 (fmt 0) or bf16 (fmt 1) A/B and fp32 D.
+// Instruction descriptor, kind::f16 with f16 (fmt 0) or bf16 (fmt 1) A/B and fp32 D:
+//   [4,6) D fmt (1=f32)  [7,10) A fmt  [10,13) B fmt  [15] A major (0=K,1=MN)  [16] B major  [17,23) N>>3  [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int fp16, int a_mn_major, int b_mn_major) {
   const uint32_t fmt = fp16 ? 0u : 1u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -445,9 +397,5 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
 enum { TMAP_BF16 = 0, TMAP_F16 = 1, TMAP_F32 = 2 };
 int encode_tmap(CUtensorMap* map, int elem /* TMAP_* */, const void* base, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes /* rank-1 entries, dims 1.. */, const uint32_t* box);
-static inline int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                                   const uint64_t* strides_bytes, const uint32_t* box) {
-  return encode_tmap(map, TMAP_BF16, base, rank, dims, strides_bytes, box);
-}
 
 }  // namespace rnamsm
