@@ -230,3 +230,31 @@ def test_streamed_extraction_equals_forward(pkg, pads):
     emb_h = torch.empty((40, 768), dtype=torch.float32).pin_memory()
     pkg.extract_features_streamed(model, tokens.pin_memory(), atp_h, emb_h)
     assert np.array_equal(atp_h.numpy(), atp) and np.array_equal(emb_h.numpy(), emb)
+
+
+def test_inference_cli_writes_reference_file_formats(pkg, tmp_path):
+    """python -m rnamsm_b200.inference (the hydra-free RNA_MSM_Inference.py): <id>_atp.npy (120, L, L) f32 and
+    <id>_emb.npy (L, 768) f32, equal to forward + extract_features on the same tokens."""
+    from rnamsm_b200 import inference
+    rng = np.random.default_rng(0)
+    L_, N_ = 23, 40
+    msa_dir = tmp_path / "results"
+    msa_dir.mkdir()
+    seqs = ["".join(rng.choice(list("AGCU-"), L_)) for _ in range(N_)]
+    with open(msa_dir / "toy.a2m_msa2", "w") as f:
+        for i, s_ in enumerate(seqs):
+            f.write(f">s{i}\n{s_}\n")
+    (tmp_path / "rna_id.txt").write_text("toy\n")
+    inference.main(["--root_path", str(tmp_path), "--MSA_path", "results", "--MSA_list", "rna_id.txt",
+                    "--max_seqs_per_msa", "16", "--sample_method", "diversity-max"])
+    atp = np.load(msa_dir / "toy_atp.npy")
+    emb = np.load(msa_dir / "toy_emb.npy")
+    assert atp.shape == (120, L_, L_) and atp.dtype == np.float32 and emb.shape == (L_, 768) and emb.dtype == np.float32
+    assert atp.min() >= 0 and atp.sum(-1).max() <= 1 + 1e-4
+    # same numbers as the module API on the tokens the ingest selected
+    model, vocab = inference.build_model(None)
+    tokens, rows = pkg.ingest_msa(str(msa_dir / "toy.a2m_msa2"), vocab, 16, sample_method="diversity-max")
+    assert tokens.shape == (16, L_ + 1) and rows[0] == 0
+    out = model(tokens.unsqueeze(0), repr_layers=[10], need_head_weights=True, want_logits=False)
+    emb2, atp2 = pkg.extract_features(out, vocab, 10)
+    assert np.array_equal(emb2, emb) and np.array_equal(atp2, atp)
