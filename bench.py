@@ -291,9 +291,8 @@ def run_ours(args):
                 pkg.extract_features_streamed(model, th, atp_host.view(-1)[:NL * H * (c - 1) ** 2].view(NL * H, c - 1, c - 1),
                                               emb_host.view(-1)[:(c - 1) * D].view(c - 1, D))
             return
-        t = tok_host.cuda(non_blocking=True)
         if shard:
-            out = sharded_forward(model, t, fused=args.fused)
+            out = sharded_forward(model, tok_host.cuda(non_blocking=True), fused=args.fused)
             if rank == 0:                                           # rank 0 owns MSA row 0 and writes the files
                 att = out["row_attentions"][..., 1:, 1:].reshape(-1, C - 1, C - 1)
                 atp_host.copy_(att, non_blocking=True)
