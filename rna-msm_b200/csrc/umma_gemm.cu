@@ -606,8 +606,9 @@ static inline int tied_tile_n(int C) { return C <= 64 ? 64 : (C <= 128 ? 128 : B
 int row_logits_splits_16(int R, int C, int H) {
   const long long tiles = (long long)H * ceil_div(C, PAIR_M) * ceil_div(C, tied_tile_n(C));
   const int pairs = g_max_pairs > 0 ? g_max_pairs : num_sms() / 2;
-  // smallest split count whose tile total fills the 74 CTA pairs in whole waves as evenly as possible
-  int want = (int)std::max<long long>(1, (pairs + tiles - 1) / tiles);
+  // fewer tiles than pairs: the LARGEST split count that still fits one wave (12 head tiles x 6 splits = 72 of 74
+  // pairs; rounding up to 7 would spill 10 tiles into a second, almost empty wave and double the time)
+  int want = (int)std::max<long long>(1, pairs / tiles);
   if (tiles > pairs) {
     // more tiles than pairs: pick the split count in [1, 4] with the best wave efficiency
     double best = 0.0;
