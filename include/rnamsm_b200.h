@@ -93,7 +93,9 @@ int rnamsm_layernorm(const float* x, const float* w, const float* b, void* y, in
  * x, W in `dtype`.  For RNAMSM_EPI_BIAS: columns [0,q_cols) are multiplied by q_scale after the
  * bias (q *= scaling, modules.py:766, 905) and, when row_mask != NULL, by (1 - row_mask[m])
  * (padded query rows zeroed, modules.py:767-772).  `out` is in `dtype` except for
- * RNAMSM_EPI_BIAS_RESIDUAL where it is the fp32 residual stream updated in place. */
+ * RNAMSM_EPI_BIAS_RESIDUAL where it is the fp32 residual stream updated in place (16-bit path: by TMA
+ * reduce-add, so `out` must not be read or written by anything else on the stream meanwhile).
+ * 16-bit path: N, K and q_cols multiples of 64; any M (tails are clipped by the TMA unit). */
 int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, int N, int K, int dtype,
                   int epilogue, float q_scale, int q_cols, const uint8_t* row_mask, void* out, void* stream);
 
@@ -103,7 +105,8 @@ int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, 
  * partial: fp32 [n_splits, H, C, C].  n_splits >= 1 row ranges are summed by K5. */
 int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, float* partial, int n_splits,
                            void* stream);
-/* Suggested split count for K4 so that the launch fills the 148 SMs. */
+/* Suggested split count for K4: as many row ranges as fit ONE wave of the launch (74 CTA pairs in the
+ * 16-bit path), at least 8 rows each. */
 int rnamsm_row_attn_splits(int R, int C, int H, int dtype);
 
 /* K5 -- sum the split partials, multiply by logit_scale (1 when q already carries the whole

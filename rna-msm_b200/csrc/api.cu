@@ -107,7 +107,7 @@ int encode_tmap(CUtensorMap* map, int elem, const void* base, int rank, const ui
 //   xn      [T, D]      compute dtype   LayerNorm output feeding the next GEMM
 //   qkvh    [T, 4D|F]   compute dtype   q|k|v (3D) + attention context (D); aliased by the FFN hidden
 //   partial [S, H, C, C] fp32           split-K tied logits
-//   probs   [H, C, ldp] compute dtype   softmax probabilities for the AV GEMM (bf16 mode only)
+//   probs   [H, C, ldp] compute dtype   softmax probabilities for the AV GEMM (16-bit paths only)
 //   map     [H, C, C]   fp32            scratch attention map when the caller does not want it
 // ---------------------------------------------------------------------------------------------
 struct Plan {

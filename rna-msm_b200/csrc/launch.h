@@ -36,7 +36,7 @@ int launch_row_softmax(const float* partial, int n_splits, int H, int C, const u
 int launch_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
                       cudaStream_t st);
 
-// Epilogue description shared by the fp32 (FFMA) and bf16 (tcgen05) linear kernels.
+// Epilogue description shared by the fp32 (FFMA) and 16-bit (tcgen05) linear kernels.
 struct LinearEpilogue {
   int kind;                 // RNAMSM_EPI_*
   const float* bias;        // [N]
