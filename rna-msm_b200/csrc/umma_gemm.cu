@@ -219,7 +219,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tmem_relinquish2();
   }
   tc_fence_before();
-  cluster_sync();
+  __syncthreads();   // CTA-local ordering of the tcgen05.alloc result (also what compute-sanitizer racecheck models)
+  cluster_sync();    // both CTAs' barriers initialised and TMEM allocated before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
