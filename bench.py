@@ -270,12 +270,19 @@ def run_ours(args):
     if farm:
         farm_host = [synthetic_tokens(R, c, seed=200 + i).pin_memory() for i, c in zip(mine, my_C)]
         farm_dev = [t.cuda() for t in farm_host]
+        # --batch-tokens > 0: short MSAs grouped into forward_batch passes; results per MSA
+        # are bit-identical to the one-forward-per-MSA farm (tests/test_gpu_model.py)
+        groups = pkg.plan_batches([(R, c) for c in my_C], args.batch_tokens) if args.batch_tokens > 0 else None
 
     def step_device():
         if shard:
             return sharded_forward(model, tok_dev, fused=args.fused)
         if farm:
             out = None
+            if groups is not None:
+                for g in groups:
+                    out = model.forward_batch([farm_dev[i] for i in g], need_head_weights=True)
+                return out
             for t in farm_dev:
                 out = model(t, repr_layers=[NL], need_head_weights=True, want_logits=False)
             return out
@@ -284,7 +291,14 @@ def run_ours(args):
     emb_host = torch.empty((C - 1, D), dtype=torch.float32).pin_memory()
     atp_host = torch.empty((NL * H, C - 1, C - 1), dtype=torch.float32).pin_memory()
 
+    if farm:                                           # per-MSA views of the pinned result buffers
+        farm_atp = [atp_host.view(-1)[:NL * H * (c - 1) ** 2].view(NL * H, c - 1, c - 1) for c in my_C]
+        farm_emb = [emb_host.view(-1)[:(c - 1) * D].view(c - 1, D) for c in my_C]
+
     def step_e2e():
+        if farm and groups is not None:                # pinned host tokens in, every MSA's emb + atp back in pinned memory
+            pkg.extract_features_batch_streamed(model, farm_host, farm_atp, farm_emb, args.batch_tokens)
+            return
         if farm:
             for th in farm_host:                       # contiguous pinned views sized for this MSA
                 c = th.shape[-1]
@@ -406,6 +420,7 @@ def run_ours(args):
             "scaling": "strong" if shard else "weak",
             "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "bf16_pure": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": desc, "R": R, "C": C, "tokens_per_step_per_gpu": tokens_per_step, "layers": NL,
+                       "batch_tokens": (args.batch_tokens if farm else None),
                        "embed_dim": D, "heads": H, "weights": "random-init (reference recipe model.py:89-101, seed 42)",
                        "precision": f"{args.precision}: 16-bit operands on tcgen05 (kind::f16), fp32 accumulate / residual "
                                     "stream / LayerNorm / softmax / exported maps" if args.precision != "fp32"
@@ -439,6 +454,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "bf16_pure", "fp32"])
+    ap.add_argument("--batch-tokens", type=int, default=0,
+                    help="cfg3 only: group the MSAs into forward_batch passes of at most this many tokens "
+                         "(0 = one forward per MSA, the reference's B=1 loop)")
     ap.add_argument("--shard", action="store_true",
                     help="N > 1: ONE deep MSA sharded over the ranks (rows for tied row attention, columns for column "
                          "attention; NCCL all-reduce + all-to-all) -> strong scaling.  Default: independent MSAs, weak.")

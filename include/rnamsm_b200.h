@@ -151,6 +151,17 @@ int rnamsm_contact_head(const float* maps, int K, int C, int start, int L, const
  * [start, start+L)^2.  seq_codes uint8 [L]: 0..3 = A,C,G,U, anything else = unknown (all-zero one-hot). */
 int rnamsm_ss_pack(const float* maps, int K, int C, int start, int L, const uint8_t* seq_codes, float* out, void* stream);
 
+/* RSA-predictor input packing: _downstream_tasks/RSA/predict.py:131-141 from the
+ * device-resident hidden states: out fp32 [n_oh + D + 1, L] (= x_train[0] after its transpose):
+ * channels 0-3 = (one-hot(seq[i] over A,C,G,U) - mu_oh) / std_oh evaluated in float64 as the reference
+ * does, then D channels (emb[i, f] - mu_emb[f]) / std_emb[f] in fp32, then a channel of ones.
+ * emb: row i at emb + i*ld (pass the final x of rnamsm_msa_forward offset past BOS, ld = D).
+ * mu_oh / std_oh: HOST arrays of 4 doubles, or both NULL for the embedding-only predictor (n_oh = 0,
+ * models/RNA-MSM_Emb).  mu_emb / std_emb: device fp32 [D].  seq_codes as for rnamsm_ss_pack.
+ * Bit-identical to the reference's numpy expression. */
+int rnamsm_rsa_pack(const float* emb, int ld, int L, int D, const uint8_t* seq_codes, const double* mu_oh,
+                    const double* std_oh, const float* mu_emb, const float* std_emb, float* out, void* stream);
+
 /* ---- MSA ingest: the step in front of the hot path, on the device ---------------
  * rnamsm_msa_clean: MSA.from_fasta's character rules (utils/align.py:311-313) as a per-row compaction.
  *   raw = the record bodies back to back (newlines allowed), offsets [N+1] (int64) delimit record n;
@@ -232,6 +243,19 @@ int rnamsm_layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
 int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int R, int C, int has_pad, int dtype,
                        float* x, float* row_attn_out, float* const* rep_out, float* logits_out, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* Several short MSAs in one pass.  tokens: the int64 grids back to back
+ * ([R[0]*C[0]] then [R[1]*C[1]] ...); R, C, has_pad: HOST arrays of n_msa entries (has_pad may be NULL);
+ * x: fp32 [sum R*C, D], holds every MSA's final hidden states in the same order on return;
+ * row_attn_out: HOST array of n_msa device pointers ([N,H,C[i],C[i]] fp32 each; NULL array or NULL entries
+ * = not wanted).  The token-local steps (LayerNorms, the six projections / FFN GEMMs per layer) run once
+ * over all tokens; the tied row attention and the column attention run per MSA with that MSA's own
+ * 1/sqrt(R[i]) (modules.py:713-715), so each MSA's results are bit-identical to its own
+ * rnamsm_msa_forward call -- this is NOT the reference's padded [B,R,C] batch.  16-bit dtypes, R[i] >= 2. */
+size_t rnamsm_batch_workspace_bytes(int n_msa, const int* R, const int* C, int D, int H, int F, int dtype);
+int rnamsm_msa_forward_batch(const rnamsm_model_weights* m, int n_msa, const int64_t* tokens, const int* R, const int* C,
+                             const uint8_t* has_pad, int dtype, float* x, float* const* row_attn_out, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* ---- one deep MSA sharded over the GPUs of a box (rna-msm_b200/sharded.py) -----------
  * The reference has no multi-GPU forward; these entry points implement the partition its math allows:

@@ -427,6 +427,22 @@ def extract_features(result: Dict[str, object], num_layers: int = NUM_LAYERS) ->
     return emb, atp
 
 
+def rsa_input(emb: np.ndarray, seq: str, mu_emb, std_emb, mu_oh=None, std_oh=None) -> np.ndarray:
+    """Input tensor of the downstream RSA predictor, _downstream_tasks/RSA/predict.py:131-141 (one-hot:
+    ``one_hot_encode`` :67-74, sklearn ``OneHotEncoder(handle_unknown='ignore')`` over ``ACGU`` = an all-zero
+    row for any other letter): ``[1, 4 + D + 1, L]`` f32.  The embedding z-score is float32 arithmetic (numpy
+    float32 arrays), the one-hot z-score float64, the concatenation float64 and the final cast back to f32 --
+    kept in that order because parity with the reference's tensor is bit-exact.  ``mu_oh=None``: the
+    embedding-only predictor (``models/RNA-MSM_Emb``), no one-hot channels."""
+    emb = (np.asarray(emb, dtype=np.float32) - np.asarray(mu_emb, dtype=np.float32)) / np.asarray(std_emb, dtype=np.float32)
+    parts = [emb, np.ones((emb.shape[0], 1))]
+    if mu_oh is not None:
+        oh = np.array([[1.0 if ch == a else 0.0 for a in "ACGU"] for ch in seq], dtype=np.float64).reshape(-1, 4)
+        parts.insert(0, (oh - np.asarray(mu_oh, dtype=np.float64)) / np.asarray(std_oh, dtype=np.float64))
+    x = np.expand_dims(np.concatenate(parts, axis=1), 0)
+    return np.ascontiguousarray(x.transpose(0, 2, 1)).astype(np.float32)
+
+
 def to_dtype(sd: Dict[str, torch.Tensor], dtype: torch.dtype) -> Dict[str, torch.Tensor]:
     out = {k: v.to(dtype) for k, v in sd.items()}
     out["lm_head.weight"] = out["embed_tokens.weight"]

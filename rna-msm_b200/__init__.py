@@ -10,10 +10,12 @@ from .model import MSATransformer  # noqa: F401
 from .modules import (AxialTransformerLayer, ColumnSelfAttention, ContactPredictionHead,  # noqa: F401
                       FeedForwardNetwork, LearnedPositionalEmbedding, NormalizedResidualBlock, RobertaLMHead,
                       RowSelfAttention)
-from .inference import extract_features, extract_features_streamed, pack_ss_input, run_inference  # noqa: F401
+from .inference import (extract_features, extract_features_batch, extract_features_batch_streamed,  # noqa: F401
+                        extract_features_streamed, pack_rsa_input, pack_ss_input, plan_batches, run_inference)
 from .ingest import ingest_msa  # noqa: F401
 
 __all__ = ["MSATransformer", "AxialTransformerLayer", "RowSelfAttention", "ColumnSelfAttention",
            "FeedForwardNetwork", "NormalizedResidualBlock", "LearnedPositionalEmbedding", "RobertaLMHead",
            "ContactPredictionHead", "Alphabet", "Vocab", "read_msa", "tokenize_msa", "extract_features",
-           "run_inference", "ingest_msa", "pack_ss_input", "extract_features_streamed"]
+           "run_inference", "ingest_msa", "pack_ss_input", "extract_features_streamed", "extract_features_batch",
+           "extract_features_batch_streamed", "pack_rsa_input", "plan_batches"]

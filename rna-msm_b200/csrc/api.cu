@@ -241,6 +241,135 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Several short MSAs in one pass.  The tokens of all MSAs sit back to back in one
+// [T_total, D] stream: the token-local work (three LayerNorms, six GEMMs per layer) is launched ONCE over
+// T_total, so a 256 x 51 alignment no longer pays a partial last wave and a pipeline ramp per GEMM; the
+// attention steps, which are per alignment by definition (tied logits sum over that MSA's rows with its
+// own 1/sqrt(R), modules.py:713-715; column attention runs over that MSA's depth), are launched per MSA on
+// its slice.  Every output element is produced by exactly the instruction sequence of the one-MSA call, so
+// the results are bit-identical to n_msa calls of rnamsm_msa_forward -- NOT the reference's padded [B,R,C]
+// batch, whose align_scaling would use the padded row count.
+// ---------------------------------------------------------------------------------------------
+struct BatchPlan {
+  size_t el;
+  long long T;
+  size_t off_xn, off_qkvh, off_partial, off_probs, off_map, off_pad, total;
+};
+
+static int make_batch_plan(int n, const int* R, const int* C, int D, int H, int F, int dtype, BatchPlan* bp) {
+  BatchPlan b{};
+  b.el = 2;
+  size_t partial = 0, probs = 0, map = 0;
+  for (int i = 0; i < n; ++i) {
+    if (R[i] < 2 || C[i] < 1) {
+      set_error("msa_forward_batch: MSA %d has R=%d C=%d (need R >= 2, C >= 1; run single-row inputs through rnamsm_msa_forward)",
+                i, R[i], C[i]);
+      return 2;
+    }
+    const Plan p = make_plan(R[i], C[i], D, H, F, dtype);
+    partial = std::max(partial, align256((size_t)p.splits * H * C[i] * C[i] * 4));
+    probs = std::max(probs, align256((size_t)H * C[i] * p.ldp * p.el));
+    map = std::max(map, align256((size_t)H * C[i] * C[i] * 4));
+    b.T += (long long)R[i] * C[i];
+  }
+  size_t o = 0;
+  b.off_xn = o;      o += align256((size_t)b.T * D * b.el);
+  b.off_qkvh = o;    o += align256((size_t)b.T * (size_t)std::max(4 * D, F) * b.el);
+  b.off_partial = o; o += partial;
+  b.off_probs = o;   o += probs;
+  b.off_map = o;     o += map;
+  b.off_pad = o;     o += align256((size_t)b.T);
+  b.total = o;
+  *bp = b;
+  return 0;
+}
+
+static int layer_forward_batch(const rnamsm_layer_weights* w, int D, int H, int F, float eps, float* x, int n,
+                               const int* R, const int* C, const uint8_t* has_pad, bool any_pad, int dtype, int layer,
+                               float* const* row_attn_out, uint8_t* ws, const BatchPlan& bp,
+                               cudaStream_t st) {
+  const long long T = bp.T;
+  const size_t el = bp.el;
+  uint8_t* xn = ws + bp.off_xn;
+  uint8_t* qkv = ws + bp.off_qkvh;
+  uint8_t* ctx = qkv + (size_t)T * 3 * D * el;
+  float* partial = reinterpret_cast<float*>(ws + bp.off_partial);
+  void* probs_lp = ws + bp.off_probs;
+  const uint8_t* pad = ws + bp.off_pad;
+  const int row_dt = block_dtype(w->row.dtype, dtype);
+  const int col_dt = block_dtype(w->col.dtype, dtype);
+  int rc;
+
+  // ---- tied row attention (same constants as layer_forward's 16-bit branch)
+  if ((rc = launch_layernorm(x, w->row.ln_w, w->row.ln_b, xn, row_dt, T, D, eps, st))) return rc;
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS, w->row.b_qkv, 0.125f, D, any_pad ? pad : nullptr};
+    if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, row_dt, e, qkv, st))) return rc;
+  }
+  long long off = 0;
+  for (int i = 0; i < n; ++i) {
+    const Plan p = make_plan(R[i], C[i], D, H, F, dtype);
+    const uint8_t* qkv_i = qkv + (size_t)off * 3 * D * el;
+    const uint8_t* pad_i = (has_pad && has_pad[i]) ? pad + off : nullptr;
+    float* map = (row_attn_out && row_attn_out[i])
+                     ? row_attn_out[i] + (size_t)layer * H * C[i] * C[i]
+                     : reinterpret_cast<float*>(ws + bp.off_map);
+    if ((rc = launch_row_logits_16(qkv_i, R[i], C[i], H, row_dt == RNAMSM_F16, partial, p.splits, st))) return rc;
+    if ((rc = launch_row_softmax(partial, p.splits, H, C[i], pad_i, 1.0f / sqrtf((float)R[i]), map, probs_lp, p.ldp,
+                                 row_dt, st)))
+      return rc;
+    if ((rc = launch_row_av_16(probs_lp, p.ldp, qkv_i, R[i], C[i], H, row_dt == RNAMSM_F16, ctx + (size_t)off * D * el,
+                               st)))
+      return rc;
+    off += (long long)R[i] * C[i];
+  }
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->row.b_out, 1.f, 0, nullptr};
+    if ((rc = linear_any(ctx, w->row.w_out, T, D, D, row_dt, e, x, st))) return rc;
+  }
+
+  // ---- column attention: LayerNorm per MSA (it transposes that MSA's token order), one QKV GEMM, flash
+  // kernel per MSA on its [C, R, 3D] slice, one out-projection.
+  off = 0;
+  for (int i = 0; i < n; ++i) {
+    const long long Ti = (long long)R[i] * C[i];
+    if ((rc = launch_layernorm(x + (size_t)off * D, w->col.ln_w, w->col.ln_b, xn + (size_t)off * D * el, col_dt, Ti, D,
+                               eps, st, R[i], C[i])))
+      return rc;
+    off += Ti;
+  }
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS, w->col.b_qkv, 1.0f / sqrtf(64.f), D, nullptr};
+    if ((rc = linear_any(xn, w->col.w_qkv, T, 3 * D, D, col_dt, e, qkv, st))) return rc;
+  }
+  off = 0;
+  for (int i = 0; i < n; ++i) {
+    const uint8_t* pad_i = (has_pad && has_pad[i]) ? pad + off : nullptr;
+    if ((rc = launch_col_attn_16(qkv + (size_t)off * 3 * D * el, R[i], C[i], H, col_dt == RNAMSM_F16, 1, pad_i,
+                                 ctx + (size_t)off * D * el, st)))
+      return rc;
+    off += (long long)R[i] * C[i];
+  }
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->col.b_out, 1.f, 0, nullptr};
+    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st))) return rc;
+  }
+
+  // ---- feed-forward over all tokens
+  if ((rc = launch_layernorm(x, w->ffn_ln_w, w->ffn_ln_b, xn, dtype, T, D, eps, st))) return rc;
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_GELU, w->fc1_b, 1.f, 0, nullptr};
+    if ((rc = linear_any(xn, w->fc1_w, T, F, D, dtype, e, qkv, st))) return rc;
+  }
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->fc2_b, 1.f, 0, nullptr};
+    if ((rc = linear_any(qkv, w->fc2_w, T, D, F, dtype, e, x, st))) return rc;
+  }
+  return 0;
+}
+
 }  // namespace rnamsm
 
 using namespace rnamsm;
@@ -396,6 +525,44 @@ int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int
     if ((rc = launch_vocab_proj(h32, m->tok_emb, m->lm_bias, (long long)T, m->vocab, D, logits_out, st))) return rc;
   }
   return 0;
+}
+
+size_t rnamsm_batch_workspace_bytes(int n_msa, const int* R, const int* C, int D, int H, int F, int dtype) {
+  BatchPlan bp;
+  if (n_msa <= 0 || !is16(dtype) || make_batch_plan(n_msa, R, C, D, H, F, dtype, &bp)) return 0;
+  return bp.total;
+}
+
+int rnamsm_msa_forward_batch(const rnamsm_model_weights* m, int n_msa, const int64_t* tokens, const int* R, const int* C,
+                             const uint8_t* has_pad, int dtype, float* x, float* const* row_attn_out, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->embed_dim, H = m->num_heads, F = m->ffn_dim, N = m->num_layers;
+  RNAMSM_REQUIRE(D == H * 64, "msa_forward_batch: head_dim must be 64 (D=%d H=%d)", D, H);
+  RNAMSM_REQUIRE(is16(dtype), "msa_forward_batch: 16-bit operand types only (dtype %d); the fp32 parity path runs one MSA per call",
+                 dtype);
+  RNAMSM_REQUIRE(n_msa >= 1 && R && C, "msa_forward_batch: empty batch");
+  BatchPlan bp;
+  int rc;
+  if ((rc = make_batch_plan(n_msa, R, C, D, H, F, dtype, &bp))) return rc;
+  RNAMSM_REQUIRE(workspace_bytes >= bp.total, "msa_forward_batch: workspace %zu < required %zu", workspace_bytes, bp.total);
+  RNAMSM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "msa_forward_batch: workspace must be 256 B aligned");
+  uint8_t* ws = (uint8_t*)workspace;
+  uint8_t* pad = ws + bp.off_pad;
+  bool any_pad = false;
+  long long off = 0;
+  for (int i = 0; i < n_msa; ++i) {
+    any_pad = any_pad || (has_pad && has_pad[i]);
+    if ((rc = launch_embed_ln(tokens + off, R[i], C[i], m->tok_emb, m->vocab, m->pos_emb, m->n_pos, m->row_pos,
+                              m->ln_before_w, m->ln_before_b, D, m->pad_idx, m->ln_eps, x + (size_t)off * D, pad + off, st)))
+      return rc;
+    off += (long long)R[i] * C[i];
+  }
+  for (int l = 0; l < N; ++l)
+    if ((rc = layer_forward_batch(&m->layers[l], D, H, F, m->ln_eps, x, n_msa, R, C, has_pad, any_pad, dtype, l,
+                                  row_attn_out, ws, bp, st)))
+      return rc;
+  return launch_layernorm(x, m->ln_after_w, m->ln_after_b, x, RNAMSM_F32, bp.T, D, m->ln_eps, st);
 }
 
 }  // extern "C"

@@ -151,3 +151,66 @@ extern "C" int rnamsm_ss_pack(const float* maps, int K, int C, int start, int L,
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// RSA-predictor input packing (_downstream_tasks/RSA/predict.py:131-141): the
+// [4 + D + 1, L] tensor (z-scored one-hot | z-scored embedding | ones, transposed to channels-first) written
+// from the device-resident hidden states.  The reference computes the embedding z-score in fp32
+// ((emb - mu) / std, numpy float32 arrays) and the one-hot z-score in float64 before the final cast to fp32;
+// both are reproduced operation for operation (__fsub_rn / __fdiv_rn: no contraction, IEEE division; the
+// eight possible one-hot values are rounded from float64 on the host), so the result is bit-identical.
+// 32 x 32 tiles through shared memory: reads coalesced along the feature axis, writes along the residue axis.
+// ---------------------------------------------------------------------------------------------------------
+namespace rnamsm {
+struct RsaOneHot { float v[8]; };  // [channel][seq[i] == channel]
+
+__global__ void __launch_bounds__(256)
+rsa_pack_kernel(const float* __restrict__ emb, int ld, int L, int D, int n_oh, const uint8_t* __restrict__ codes,
+                const float* __restrict__ mu, const float* __restrict__ sd, RsaOneHot oh, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.x * 32, ch0 = blockIdx.y * 32, n_ch = n_oh + D + 1;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = ch0 + tx;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int i = i0 + ty + k;
+    float v = 0.f;
+    if (i < L && ch < n_ch) {
+      if (ch < n_oh) {
+        v = oh.v[ch * 2 + (codes[i] == ch ? 1 : 0)];
+      } else if (ch < n_oh + D) {
+        const int f = ch - n_oh;
+        v = __fdiv_rn(__fsub_rn(emb[(size_t)i * ld + f], mu[f]), sd[f]);
+      } else {
+        v = 1.f;
+      }
+    }
+    tile[ty + k][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int c = ch0 + ty + k, i = i0 + tx;
+    if (c < n_ch && i < L) out[(size_t)c * L + i] = tile[tx][ty + k];
+  }
+}
+}  // namespace rnamsm
+
+extern "C" int rnamsm_rsa_pack(const float* emb, int ld, int L, int D, const uint8_t* seq_codes, const double* mu_oh,
+                               const double* std_oh, const float* mu_emb, const float* std_emb, float* out,
+                               void* stream) {
+  RNAMSM_REQUIRE(L > 0 && D > 0 && ld >= D, "rsa_pack: bad shape (L=%d D=%d ld=%d)", L, D, ld);
+  RNAMSM_REQUIRE((mu_oh == nullptr) == (std_oh == nullptr), "rsa_pack: mu_oh and std_oh go together");
+  RNAMSM_REQUIRE(mu_oh == nullptr || seq_codes != nullptr, "rsa_pack: one-hot channels need the sequence codes");
+  rnamsm::RsaOneHot oh{};
+  const int n_oh = mu_oh ? 4 : 0;
+  for (int c = 0; c < n_oh; ++c)
+    for (int hit = 0; hit < 2; ++hit) oh.v[c * 2 + hit] = (float)(((double)hit - mu_oh[c]) / std_oh[c]);
+  dim3 grid(rnamsm::ceil_div(L, 32), rnamsm::ceil_div(n_oh + D + 1, 32));
+  RNAMSM_REQUIRE(grid.y <= 65535, "rsa_pack: D too large");
+  rnamsm::rsa_pack_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(emb, ld, L, D, n_oh, seq_codes, mu_emb, std_emb,
+                                                                         oh, out);
+  rnamsm::count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

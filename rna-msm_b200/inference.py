@@ -102,12 +102,119 @@ def pack_ss_input(row_attentions: torch.Tensor, sequence: str, prepend_bos: bool
     Ls = Cc - start
     if len(sequence) != Ls:
         raise ValueError(f"sequence length {len(sequence)} != map size {Ls}")
-    codes = torch.tensor([{"A": 0, "C": 1, "G": 2, "U": 3}.get(ch, 255) for ch in sequence], dtype=torch.uint8,
-                         device=row_attentions.device)
+    codes = torch.tensor([_SEQ_CODES.get(ch, 255) for ch in sequence], dtype=torch.uint8, device=row_attentions.device)
     maps = row_attentions[0].float().contiguous()
     out = torch.empty((1, 8 + N * H, Ls, Ls), dtype=torch.float32, device=maps.device)
     with torch.cuda.device(maps.device):
         L.check(L.lib.rnamsm_ss_pack(L.ptr(maps), N * H, Cc, start, Ls, L.ptr(codes), L.ptr(out), L.stream_ptr()), "ss_pack")
+    return out
+
+
+@torch.no_grad()
+def extract_features_batch_streamed(model: MSATransformer, tokens_list, atp_hosts, emb_hosts,
+                                    token_budget: int = 262144) -> None:
+    """``extract_features_batch`` with host buffers on both sides: ``tokens_list[i]`` ``[1, R_i, C_i]`` (pinned host
+    or device), ``atp_hosts[i]`` ``[(N*H), L_i, L_i]`` and ``emb_hosts[i]`` ``[L_i, D]`` pinned fp32.  Each group's
+    device->host copies run on a side stream while the next group computes.  Returns when every buffer is complete."""
+    vocab, N, H = model.vocab, model.num_layers, model.num_attention_heads
+    start = int(vocab.prepend_bos)
+    shapes = [tuple(t.shape[-2:]) for t in tokens_list]
+    with torch.cuda.device(model.device):
+        main = torch.cuda.current_stream()
+        side = getattr(model, "_copy_stream", None)
+        if side is None:
+            side = model._copy_stream = torch.cuda.Stream()
+        for batch in plan_batches(shapes, token_budget):
+            res = model.forward_batch([tokens_list[i].to(model.device, non_blocking=True) for i in batch],
+                                      need_head_weights=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                for i, r in zip(batch, res):
+                    Ls = shapes[i][1] - start - int(vocab.append_eos)
+                    att, rep = r["row_attentions"], r["representations"][N]
+                    atp_hosts[i].copy_(att[0, :, :, start:start + Ls, start:start + Ls].reshape(N * H, Ls, Ls),
+                                       non_blocking=True)
+                    emb_hosts[i].copy_(rep[0, 0, start:start + Ls], non_blocking=True)
+                    att.record_stream(side)
+                    rep.record_stream(side)
+        side.synchronize()
+        main.synchronize()
+
+
+_SEQ_CODES = {"A": 0, "C": 1, "G": 2, "U": 3}
+
+
+@torch.no_grad()
+def pack_rsa_input(representation: torch.Tensor, sequence: str, mu_emb, std_emb, mu_oh=None, std_oh=None,
+                   prepend_bos: bool = True) -> torch.Tensor:
+    """The ``[1, 4 + D + 1, L]`` input of the downstream RSA predictor (``_downstream_tasks/RSA/predict.py:131-141``:
+    z-scored one-hot | z-scored embedding | ones, channels first) built on the device from
+    ``representations[num_layers]`` ``[1, R, C, D]`` -- no ``*_emb.npy`` round trip.  ``mu_*`` / ``std_*`` are the
+    arrays of the predictor's ``statistic_dict_{oh,emb}.pickle``; without ``mu_oh`` the one-hot channels are left
+    out (the embedding-only predictor, ``models/RNA-MSM_Emb``).  Bit-identical to the reference's expression."""
+    import ctypes as C
+    from . import _lib as L
+    L.require_cuda(representation, "representation")
+    assert representation.ndim == 4 and representation.shape[0] == 1
+    _, R, Cc, D = representation.shape
+    start = int(prepend_bos)
+    Ls = Cc - start
+    if len(sequence) != Ls:
+        raise ValueError(f"sequence length {len(sequence)} != embedding length {Ls}")
+    if (mu_oh is None) != (std_oh is None):
+        raise ValueError("mu_oh and std_oh go together")
+    dev = representation.device
+    x = representation.float().contiguous()
+    codes = torch.tensor([_SEQ_CODES.get(ch, 255) for ch in sequence], dtype=torch.uint8, device=dev)
+    mu = torch.as_tensor(np.asarray(mu_emb, dtype=np.float32)).to(dev)
+    sd = torch.as_tensor(np.asarray(std_emb, dtype=np.float32)).to(dev)
+    if mu.numel() != D or sd.numel() != D:
+        raise ValueError(f"mu_emb / std_emb must have {D} entries")
+    n_oh = 4 if mu_oh is not None else 0
+    oh_mu = (C.c_double * 4)(*np.asarray(mu_oh, dtype=np.float64).tolist()) if n_oh else None
+    oh_sd = (C.c_double * 4)(*np.asarray(std_oh, dtype=np.float64).tolist()) if n_oh else None
+    out = torch.empty((1, n_oh + D + 1, Ls), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib.rnamsm_rsa_pack(x[0, 0, start:].data_ptr(), D, Ls, D, L.ptr(codes), oh_mu, oh_sd, L.ptr(mu), L.ptr(sd),
+                                      L.ptr(out), L.stream_ptr()), "rsa_pack")
+    return out
+
+
+def plan_batches(shapes, token_budget: int = 262144):
+    """Group MSAs ``[(R, C), ...]`` for ``MSATransformer.forward_batch``: largest first, each batch filled with
+    the largest remaining alignments that still fit ``token_budget`` tokens (an alignment above the budget
+    runs alone).  Returns lists of indices into ``shapes``; every index appears exactly once."""
+    order = sorted(range(len(shapes)), key=lambda i: -shapes[i][0] * shapes[i][1])
+    batches, used = [], [False] * len(shapes)
+    for i in order:
+        if used[i]:
+            continue
+        used[i] = True
+        batch, room = [i], token_budget - shapes[i][0] * shapes[i][1]
+        for j in order:
+            t = shapes[j][0] * shapes[j][1]
+            if not used[j] and t <= room:
+                used[j] = True
+                batch.append(j)
+                room -= t
+        batches.append(batch)
+    return batches
+
+
+@torch.no_grad()
+def extract_features_batch(model: MSATransformer, tokens_list, token_budget: int = 262144):
+    """``RNA_MSM_Inference.py:147-166`` for many MSAs: grouped by ``plan_batches`` and run through
+    ``forward_batch``; returns ``[(emb (L_i, D), atp (N*H, L_i, L_i)), ...]`` as numpy arrays in input order,
+    identical to calling ``extract_features(model(tokens_i, ...))`` one MSA at a time."""
+    vocab, N = model.vocab, model.num_layers
+    shapes = [tuple(t.shape[-2:]) for t in tokens_list]
+    out = [None] * len(tokens_list)
+    for batch in plan_batches(shapes, token_budget):
+        res = model.forward_batch([tokens_list[i].to(model.device) for i in batch], need_head_weights=True)
+        for i, r in zip(batch, res):
+            out[i] = extract_features(r, vocab, N)
     return out
 
 

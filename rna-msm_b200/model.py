@@ -199,3 +199,73 @@ class MSATransformer(nn.Module, _PrecisionMixin):
             if return_contacts:
                 result["contacts"] = self.contact_head(tokens, row_att)
         return result
+
+    @torch.no_grad()
+    def forward_batch(self, tokens_list, need_head_weights: bool = False):
+        """Several MSAs of different shapes in ONE pass (``rnamsm_msa_forward_batch``).
+
+        ``tokens_list``: ``[1, R_i, C_i]`` (or ``[R_i, C_i]``) int64 grids.  Returns one dict per MSA with
+        ``representations[num_layers]`` ``[1, R_i, C_i, D]`` and (optionally) ``row_attentions``
+        ``[1, N, H, C_i, C_i]`` -- bit-identical to ``forward`` called on each MSA alone (each MSA keeps its own
+        ``1/sqrt(R_i)`` in the tied attention, modules.py:713-715), unlike the reference's padded ``[B, R, C]``
+        batch.  The token-local kernels run once over all MSAs' tokens, which is what makes short alignments
+        (256 x 51) fill the GPU.  16-bit precisions; the fp32 parity path and single-row inputs go one by one."""
+        _infer_only(self)
+        grids = []
+        for t in tokens_list:
+            t = t[0] if t.ndim == 3 and t.shape[0] == 1 else t
+            assert t.ndim == 2, "forward_batch takes one MSA per entry ([1,R,C] or [R,C])"
+            L.require_cuda(t, "tokens")
+            if t.device != self.device:
+                raise RuntimeError(f"tokens on {t.device} but model on {self.device}")
+            grids.append(t.long().contiguous())
+        if not grids:
+            return []
+        N, D, H = self.num_layers, self.embed_dim, self.num_attention_heads
+        code = self._code
+        if code == L.dtype_code("fp32") or any(g.shape[0] < 2 for g in grids):
+            outs = []
+            for g in grids:
+                r = self.forward(g.unsqueeze(0), repr_layers=[N], need_head_weights=need_head_weights, want_logits=False)
+                outs.append({"representations": {N: r["representations"][N]}, **(
+                    {"row_attentions": r["row_attentions"]} if need_head_weights else {})})
+            return outs
+        dev = self.device
+        L.device_check(dev)
+        n = len(grids)
+        Rs, Cs = [g.shape[0] for g in grids], [g.shape[1] for g in grids]
+        for R, Cc in zip(Rs, Cs):
+            if self.msa_position_embedding is not None and R > 1024:       # model.py:354-359
+                raise RuntimeError(
+                    "Using model with MSA position embedding trained on maximum MSA "
+                    f"depth of 1024, but received {R} alignments.")
+        flat = torch.cat([g.reshape(-1) for g in grids])
+        is_pad = flat.eq(self.vocab.pad_idx)
+        sizes = [R * Cc for R, Cc in zip(Rs, Cs)]
+        pad_counts = torch.stack([c.sum() for c in is_pad.split(sizes)]).tolist()      # one host sync for the batch
+        for g, cnt, Cc in zip(grids, pad_counts, Cs):
+            n_nonpad_max = int((~g.eq(self.vocab.pad_idx)).sum(-1).max()) if cnt else Cc
+            if n_nonpad_max + self.vocab.pad_idx >= self.embed_positions.weight.shape[0]:
+                raise IndexError(
+                    f"sequence length {Cc} exceeds the {self.embed_positions.max_positions} learned positions")
+        has_pad = bytes(1 if c else 0 for c in pad_counts)
+        T = sum(sizes)
+        x = torch.empty((T, D), dtype=torch.float32, device=dev)
+        maps = [torch.empty((1, N, H, Cc, Cc), dtype=torch.float32, device=dev) for Cc in Cs] if need_head_weights else None
+        with torch.cuda.device(dev):
+            m = self.c_weights(code)
+            Ra, Ca = (C.c_int * n)(*Rs), (C.c_int * n)(*Cs)
+            nbytes = L.lib.rnamsm_batch_workspace_bytes(n, Ra, Ca, D, H, 4 * D, code)
+            if nbytes == 0:
+                raise RuntimeError("rnamsm_batch_workspace_bytes: " + L.lib.rnamsm_last_error().decode(errors="replace"))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            map_ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in maps]) if maps is not None else None
+            L.check(L.lib.rnamsm_msa_forward_batch(C.byref(m), n, L.ptr(flat), Ra, Ca, has_pad, code, L.ptr(x), map_ptrs,
+                                                   L.ptr(ws), nbytes, L.stream_ptr()), "msa_forward_batch")
+        outs = []
+        for i, xi in enumerate(x.split(sizes)):
+            o = {"representations": {N: xi.view(1, Rs[i], Cs[i], D)}}
+            if maps is not None:
+                o["row_attentions"] = maps[i]
+            outs.append(o)
+        return outs

@@ -232,6 +232,59 @@ def test_streamed_extraction_equals_forward(pkg, pads):
     assert np.array_equal(atp_h.numpy(), atp) and np.array_equal(emb_h.numpy(), emb)
 
 
+# ------------------------------------------------------------------------------ many short MSAs per pass (8f row 4)
+BATCH_SHAPES = [(33, 41, 2), (7, 36, 0), (140, 20, 0), (260, 70, 0), (2, 9, 1)]     # (R, C, padded columns)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_forward_batch_equals_single_forwards(pkg, precision):
+    """forward_batch (token-local kernels once over all MSAs, attention per MSA with its own 1/sqrt(R)) is
+    bit-identical to one forward per MSA -- and therefore NOT the reference's padded-batch result."""
+    model, _ = build(pkg, 9, 3, 2.0, precision)
+    toks = [O.make_tokens(R, C, 20 + i, pad_cols=p).cuda() for i, (R, C, p) in enumerate(BATCH_SHAPES)]
+    outs = model.forward_batch(toks, need_head_weights=True)
+    assert len(outs) == len(toks)
+    for t, o in zip(toks, outs):
+        one = model(t, repr_layers=[3], need_head_weights=True, want_logits=False)
+        d_rep = (o["representations"][3] - one["representations"][3]).abs().max().item()
+        d_att = (o["row_attentions"] - one["row_attentions"]).abs().max().item()
+        assert o["representations"][3].shape == one["representations"][3].shape
+        assert d_rep == 0.0 and d_att == 0.0, (tuple(t.shape), d_rep, d_att)
+    no_maps = model.forward_batch(toks[:2])
+    assert "row_attentions" not in no_maps[0]
+    assert torch.equal(no_maps[1]["representations"][3], outs[1]["representations"][3])
+
+
+def test_forward_batch_vs_oracle_and_routing(pkg):
+    """The batch entry against the CPU oracle (per-MSA tied scaling), the one-by-one route taken by the fp32 path
+    and by single-row inputs, batched extraction, and the error behaviour."""
+    model, sd = build(pkg, 9, 2, 2.0, "fp16")
+    shapes = [(12, 30, 0), (40, 17, 3), (1, 22, 0)]
+    toks = [O.make_tokens(R, C, 40 + i, pad_cols=p) for i, (R, C, p) in enumerate(shapes)]
+    outs = model.forward_batch([t.cuda() for t in toks[:2]], need_head_weights=True)
+    for t, o in zip(toks, outs):
+        ref = O.forward(sd, t, repr_layers=[2], need_head_weights=True, num_layers=2, want_logits=False)
+        assert O.rel_err(o["representations"][2].cpu(), ref["representations"][2]) < BF16_TOL
+        assert O.rel_err(o["row_attentions"].cpu(), ref["row_attentions"]) < BF16_TOL
+    feats = pkg.extract_features_batch(model, toks, token_budget=600)          # forces several groups + the R = 1 route
+    for t, (emb, atp) in zip(toks, feats):
+        one = model(t.cuda(), repr_layers=[2], need_head_weights=True, want_logits=False)
+        emb1, atp1 = pkg.extract_features(one, model.vocab, 2)
+        assert np.array_equal(emb, emb1) and np.array_equal(atp, atp1)
+    atp_h = [torch.empty((2 * 12, C - 1, C - 1), dtype=torch.float32).pin_memory() for _, C, _ in shapes]
+    emb_h = [torch.empty((C - 1, 768), dtype=torch.float32).pin_memory() for _, C, _ in shapes]
+    pkg.extract_features_batch_streamed(model, [t.pin_memory() for t in toks], atp_h, emb_h, token_budget=1100)
+    for (emb, atp), a, e in zip(feats, atp_h, emb_h):
+        assert np.array_equal(a.numpy(), atp) and np.array_equal(e.numpy(), emb)
+    m32, _ = build(pkg, 9, 2, 2.0, "fp32")
+    o32 = m32.forward_batch([toks[0].cuda()], need_head_weights=True)[0]
+    one = m32(toks[0].cuda(), repr_layers=[2], need_head_weights=True, want_logits=False)
+    assert torch.equal(o32["row_attentions"], one["row_attentions"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.forward_batch([toks[0]])
+    assert model.forward_batch([]) == []
+
+
 def test_inference_cli_writes_reference_file_formats(pkg, tmp_path):
     """python -m rnamsm_b200.inference (the hydra-free RNA_MSM_Inference.py): <id>_atp.npy (120, L, L) f32 and
     <id>_emb.npy (L, 768) f32, equal to forward + extract_features on the same tokens."""

@@ -259,3 +259,25 @@ def test_ss_input_packing_matches_reference(golden_dir):
     x = pkg.pack_ss_input(ra.cuda(), seq)
     assert tuple(x.shape) == want.shape == (1, 128, Ls, Ls) and x.dtype == torch.float32
     assert torch.equal(x.cpu(), torch.from_numpy(want))                    # bit-exact: copies and 0/1
+
+
+# ------------------------------------------------------------------------------------------ RSA input packing (8f row 4)
+def test_rsa_input_packing_matches_reference(golden_dir):
+    """pack_rsa_input vs the [1,773,L] tensor obtained by executing the reference's own packing statements
+    (oracle/gen_golden_rsa.py), bit-exact; and the embedding-only variant vs the oracle."""
+    import os
+    import rnamsm_b200 as pkg
+    g = np.load(os.path.join(golden_dir, "rsa_pack.npz"))
+    seq, emb, want = str(g["seq"]), g["emb"], g["x"]
+    Ls = len(seq)
+    rep = torch.zeros(1, 3, Ls + 1, 768)
+    rep[0, 0, 1:] = torch.from_numpy(emb)                                   # MSA row 0 with the BOS column back in
+    rep[0, 1:] = 7.0                                                        # other rows must not be read
+    x = pkg.pack_rsa_input(rep.cuda(), seq, g["mu_emb"], g["std_emb"], g["mu_oh"], g["std_oh"])
+    assert tuple(x.shape) == want.shape == (1, 773, Ls) and x.dtype == torch.float32
+    assert torch.equal(x.cpu(), torch.from_numpy(want))
+    x0 = pkg.pack_rsa_input(rep.cuda(), seq, g["mu_emb"], g["std_emb"])
+    assert torch.equal(x0.cpu(), torch.from_numpy(O.rsa_input(emb, seq, g["mu_emb"], g["std_emb"])))
+    with pytest.raises(ValueError):
+        pkg.pack_rsa_input(rep.cuda(), seq[:-1], g["mu_emb"], g["std_emb"])
+

@@ -113,3 +113,20 @@ def test_shipped_fixture_format():
     assert emb.shape == (35, 768) and emb.dtype == np.float32
     ss = np.load("/root/reference/_downstream_tasks/SS/inputs/attention_map/6XJQ_A.npy")
     assert ss.shape == (120, 58, 58) and ss.dtype == np.float32
+
+
+def test_plan_batches_covers_every_msa_once_within_budget():
+    """Grouping policy of extract_features_batch (8f row 4): every MSA exactly once, groups within the token
+    budget unless a single alignment exceeds it, largest alignment first."""
+    import random
+    from rnamsm_b200.inference import plan_batches
+    rnd = random.Random(3)
+    shapes = [(256, rnd.randint(51, 501)) for _ in range(64)] + [(512, 600)]
+    groups = plan_batches(shapes, 262144)
+    assert sorted(i for g in groups for i in g) == list(range(len(shapes)))
+    for g in groups:
+        tok = sum(shapes[i][0] * shapes[i][1] for i in g)
+        assert tok <= 262144 or len(g) == 1
+    assert groups[0] == [64]                                               # 307200 tokens: alone, first
+    assert len(groups) < len(shapes) // 2                                  # short alignments do get grouped
+    assert plan_batches([], 10) == []

@@ -129,3 +129,15 @@ def test_read_a2m_matches_shipped_msa(golden_dir):
     _, tok = O.read_a2m("/root/reference/results/2DRB_1.a2m_msa2", 512)
     g = load(golden_dir, "2DRB_1")
     assert np.array_equal(tok.numpy(), g["tokens"][0].astype(np.int64))
+
+
+def test_oracle_rsa_input_matches_reference(golden_dir):
+    """oracle rsa_input vs the tensor produced by executing the reference's own packing statements
+    (oracle/gen_golden_rsa.py): bit-exact, including the float64 -> f32 one-hot z-scores."""
+    g = load(golden_dir, "rsa_pack")
+    x = O.rsa_input(g["emb"], str(g["seq"]), g["mu_emb"], g["std_emb"], g["mu_oh"], g["std_oh"])
+    assert x.shape == g["x"].shape == (1, 773, len(str(g["seq"]))) and x.dtype == np.float32
+    assert np.array_equal(x, g["x"])
+    x0 = O.rsa_input(g["emb"], str(g["seq"]), g["mu_emb"], g["std_emb"])
+    assert np.array_equal(x0[0], g["x"][0, 4:])
+
