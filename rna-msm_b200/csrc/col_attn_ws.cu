@@ -222,7 +222,10 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       int o_j = 0, o_stage = 0;
       if (total_steps > 0) issue_s();
       for (long long g = 0; g < total_steps; ++g) {
-        if (g + 1 < total_steps) issue_s();
+        // S(g+1) goes out before PV(g) -- except across an item boundary: the next item's first S waits for its Q
+        // tile, and PV(last) (which the softmax warps need for their epilogue) must not queue behind that wait
+        const bool s_new_item = K::kQBufs == 1 && s_j == 0;      // (double-buffered Q is already there: keep S ahead)
+        if (g + 1 < total_steps && !s_new_item) issue_s();
         const uint32_t va = smem_u32(smem + K::OFF_KV + o_stage * 2 * KV_BYTES + KV_BYTES);
         mbar_wait_relaxed(&p_full[t], (uint32_t)(g & 1));                  // P_t(g) in smem, O_t rescaled if needed
         tc_fence_after();
@@ -234,6 +237,7 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         umma_commit(&kv_empty[o_stage]);                           // this tile is done with K_j and V_j
         if (++o_j == nblk) o_j = 0;
         if (++o_stage == kKvStages) o_stage = 0;
+        if (g + 1 < total_steps && s_new_item) issue_s();
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * NT) {
