@@ -51,8 +51,8 @@ WORKLOADS = {
 
 def measured_traffic(workload, precision):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class, from the committed
-    ncu --set full capture of the same workload (profiles/r01c_traffic.json); None for other workloads."""
-    p = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    ncu --set full capture of the same workload (profiles/r01e_traffic.json); None for other workloads."""
+    p = os.path.join(ROOT, "profiles", "r01e_traffic.json")
     try:
         d = json.load(open(p))
         if d.get("workload") == workload and d.get("precision") == precision:
@@ -395,7 +395,7 @@ def run_ours(args):
             "avg_launch_ms": gemm_ms / max(1, gemm_launches), "launches": gemm_launches,
             "share_of_kernel_time": round(gemm_ms / kernel_ms_total, 4) if kernel_ms_total else None,
             "traffic": measured_traffic(args.workload, args.precision)[0] if not (shard or farm) else None,
-            "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01c_traffic.json)",
+            "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01e_traffic.json)",
             "algorithmic_bytes_per_launch": measured_traffic(args.workload, args.precision)[1] if not (shard or farm) else None,
             "class_time_share": shares, "class_tflops": tflops,
             "whole_forward_tflops_per_gpu": round((sum(total_flops(R, c) for c in my_C) if farm else total_flops(R, C) / (world if shard else 1))

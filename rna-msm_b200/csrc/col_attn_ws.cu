@@ -12,7 +12,10 @@
 // (~2200 per 4-tile step) at once, with 4-5 warps per scheduler to hide the FFMA -> MUFU -> FADD
 // chains.  NT = 4 fills TMEM (4 x (64 S + 64 O) = 512 columns); NT = 2 serves shallow MSAs (R <= 256).
 // Variants tried and measured equal or slower: two threads per row, one issuing thread for all
-// tiles, P through tensor memory (tcgen05.st + A-from-TMEM PV MMA), back-off in the role threads.
+// tiles, P through tensor memory (tcgen05.st + A-from-TMEM PV MMA), back-off in the role threads,
+// offsetting the tiles' phases by 400-1600 cycles.  What did cost time was the ITEM boundary
+// (t_item ~= (3.3 + steps) * t_step): direct per-thread global stores of O were 19 % of the kernel at
+// R = 512 -- O now leaves through shared memory and one asynchronous TMA store per warp.
 // Items are numbered with the query block innermost, so CTAs working at the same moment share K/V
 // through L2.
 //
