@@ -1,7 +1,7 @@
 """torchrun debug driver for the fused sharded schedule: prints progress, dumps stacks if it stalls."""
 import faulthandler, os, sys, time
 import torch, torch.distributed as dist
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 faulthandler.dump_traceback_later(50, exit=True)
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))

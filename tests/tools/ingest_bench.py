@@ -3,7 +3,7 @@
 the reference (numpy / scipy calls of utils/align.py:128-148) on a synthetic alignment."""
 import os, sys, time, tempfile
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import rnamsm_b200 as pkg
 from rnamsm_b200.ingest import ingest_msa

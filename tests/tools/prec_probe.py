@@ -1,12 +1,15 @@
+"""Diagnostic (GPU): error of each precision mode on BASELINE config 1 (2DRB_1) against the CPU oracle -- the numbers
+quoted in tests/test_gpu_model.py's header.  Lives under tests/ because it uses the oracle as the checker."""
 import os, sys, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 import rnamsm_b200 as pkg
 from oracle import msa_ref as O
 def argmax_agreement(a, b):
     a = torch.as_tensor(a).reshape(-1, a.shape[-1]); b = torch.as_tensor(b).reshape(-1, b.shape[-1])
     return float((a.argmax(-1) == b.argmax(-1)).float().mean())
 vocab = pkg.Vocab(pkg.Alphabet())
-g = np.load("/root/repo/tests/golden/2DRB_1.npz")
+g = np.load(os.path.join(ROOT, "tests", "golden", "2DRB_1.npz"))
 tokens = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
 sd = O.make_weights(int(g["wseed"]), sharpen=float(g["sharpen"]))
 for prec in ("bf16_pure", "bf16", "fp16", "fp32"):
