@@ -42,6 +42,21 @@ def test_measured_arm_does_not_import_the_oracle():
     assert t.shape == (1, 5, 7) and int(t[0, :, 0].abs().sum()) == 0 and int(t[0, :, 1:].min()) >= 4 and int(t.max()) <= 10
 
 
+def test_product_tree_never_imports_the_oracle():
+    """The package, the kernels' build script and tools/ must not import, link or execute anything under oracle/
+    (only tests/, __graft_entry__.smoke() and bench's CPU legs may)."""
+    import glob
+    import re
+    files = (glob.glob(os.path.join(ROOT, "rna-msm_b200", "**", "*.py"), recursive=True)
+             + glob.glob(os.path.join(ROOT, "rna-msm_b200", "csrc", "*"))
+             + glob.glob(os.path.join(ROOT, "tools", "**", "*.py"), recursive=True)
+             + glob.glob(os.path.join(ROOT, "include", "*.h")))
+    assert len(files) > 20
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle)|oracle[./]msa|msa_ref|msa_ingest_ref", re.M)
+    bad = [f for f in files if os.path.isfile(f) and pat.search(open(f, errors="replace").read())]
+    assert not bad, bad
+
+
 def test_reference_arm_json_contract():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
                         "0", "--workload", "cfg1"], capture_output=True, text=True, timeout=600)
