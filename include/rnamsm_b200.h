@@ -21,12 +21,14 @@
  *     operands on the tcgen05 tensor cores (kind::f16, same rate for both element types) with
  *     fp32 accumulation and an fp32 residual stream / LayerNorm / softmax (<=2e-2).  In the
  *     whole-layer drivers each attention block carries its own operand type
- *     (rnamsm_attn_weights.dtype): the production "bf16" path runs the tied row-attention block
- *     in fp16 -- its logits are sums over R*64 products whose rounding errors add coherently on
- *     redundant MSAs, and fp16's three extra mantissa bits bring the exported maps from 4.5e-2
- *     to <1e-2 on the 2DRB_1 MSA at no cost in speed.  There is no CPU fallback.
+ *     (rnamsm_attn_weights.dtype).  Production precision is fp16 everywhere.  The optional "bf16"
+ *     mode still runs the tied row-attention block in fp16: its logits are sums over R*64 products
+ *     whose rounding errors add coherently on redundant MSAs (exported maps on the 2DRB_1 MSA:
+ *     all-bf16 5.1e-2, bf16 with the fp16 row block 2.7e-2, fp16 5.4e-3; same tensor-core rate).
+ *     There is no CPU fallback.
  *   - one MSA per call (B = 1): the reference never batches MSAs (RNA_MSM_Inference.py:147)
  *     and its tied-attention scaling depends on the padded row count (modules.py:713-715).
+ *     rnamsm_msa_forward_batch runs several MSAs in one pass with exactly these per-MSA semantics.
  *   - activations are token-major: x[(r*C + c)*D + f], i.e. the reference's [R,C,B=1,D].
  */
 #ifndef RNAMSM_B200_H_
