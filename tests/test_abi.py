@@ -54,6 +54,30 @@ def test_workspace_bytes_is_pure_host_math():
     assert _lib.lib.rnamsm_workspace_bytes(0, 64, 768, 12, 3072, _lib.BF16) == 0
 
 
+def test_batch_workspace_bytes_is_pure_host_math():
+    """rnamsm_batch_workspace_bytes: token-proportional regions sum over the MSAs, the per-MSA attention scratch is
+    the maximum; invalid batches (fp32, a single-row MSA) report 0 with a message instead of a size."""
+    import ctypes as C
+    from rnamsm_b200 import _lib
+
+    def size(shapes, code=_lib.F16):
+        n = len(shapes)
+        R = (C.c_int * n)(*[s[0] for s in shapes])
+        Cc = (C.c_int * n)(*[s[1] for s in shapes])
+        return _lib.lib.rnamsm_batch_workspace_bytes(n, R, Cc, 768, 12, 3072, code)
+
+    one = size([(64, 40)])
+    single = _lib.lib.rnamsm_workspace_bytes(64, 40, 768, 12, 3072, _lib.F16)
+    assert one % 256 == 0 and single < one <= single + 64 * 40 + 512          # + the pad flags of the batch entry
+    two = size([(64, 40), (64, 40)])
+    tok = 64 * 40 * (768 * 2 + 3072 * 2 + 1)                                   # xn + qkv|ctx / FFN hidden + pad, per MSA
+    assert abs((two - one) - tok) <= 3 * 256                                   # attention scratch is shared, not doubled
+    assert size([(64, 40), (32, 90)]) > size([(64, 40), (32, 40)])             # ... and sized by the widest MSA
+    assert size([(64, 40)], _lib.F32) == 0
+    assert size([(64, 40), (1, 40)]) == 0
+    assert b"R >= 2" in _lib.lib.rnamsm_last_error()
+
+
 def test_sass_contains_blackwell_tensor_and_tma_instructions():
     """The shipped .so really is a tcgen05/TMA build (UTCHMMA / UTMALDG / LDTM in SASS)."""
     import shutil

@@ -80,6 +80,8 @@ def test_no_cpu_fallback(pkg):
         layer(torch.zeros(2, 3, 1, 768))
     with pytest.raises(RuntimeError, match="CUDA"):
         layer.feed_forward_layer.layer(torch.zeros(2, 3, 1, 768))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.forward_batch([tokens, tokens])
     with pytest.raises(ValueError):
         pkg.RowSelfAttention(768, 8)          # head_dim must be 64
     with pytest.raises(ValueError):
