@@ -132,3 +132,45 @@ def test_plan_batches_covers_every_msa_once_within_budget():
     assert groups[0] == [64]                                               # 307200 tokens: alone, first
     assert len(groups) < len(shapes) // 2                                  # short alignments do get grouped
     assert plan_batches([], 10) == []
+
+
+def test_plan_batches_properties():
+    """hypothesis: any list of shapes and any budget -> a partition of the indices; no group over budget unless it
+    is a single alignment; groups ordered by their largest member (largest first)."""
+    from hypothesis import given, settings, strategies as st
+    from rnamsm_b200.inference import plan_batches
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.tuples(st.integers(1, 1024), st.integers(1, 1024)), max_size=40), st.integers(1, 1 << 20))
+    def check(shapes, budget):
+        groups = plan_batches(shapes, budget)
+        assert sorted(i for g in groups for i in g) == list(range(len(shapes)))
+        tok = lambda i: shapes[i][0] * shapes[i][1]
+        for g in groups:
+            assert len(g) == 1 or sum(tok(i) for i in g) <= budget
+            assert tok(g[0]) == max(tok(i) for i in g)
+        heads = [tok(g[0]) for g in groups]
+        assert heads == sorted(heads, reverse=True)
+
+    check()
+
+
+def test_shard_plan_properties():
+    """hypothesis: the row / column ranges of the ranks tile the grid exactly, and the traffic model is symmetric."""
+    from hypothesis import given, settings, strategies as st
+    from rnamsm_b200.sharded import ShardPlan
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.integers(1, 8), st.integers(1, 64), st.integers(1, 64))
+    def check(n, a, b):
+        R, C = a * n, b * n
+        plans = [ShardPlan(R, C, n, r) for r in range(n)]
+        rows = [i for p in plans for i in range(R)[p.rows()]]
+        cols = [i for p in plans for i in range(C)[p.cols()]]
+        assert rows == list(range(R)) and cols == list(range(C))
+        assert all(p.rows(g) == plans[g].rows() and p.cols(g) == plans[g].cols() for p in plans for g in range(n))
+        by = plans[0].bytes_per_layer()
+        assert by["all_to_all_fwd"] == by["all_to_all_back"] == (R // n) * C * 768 * 2 * (n - 1) // n
+        assert (by["logit_all_reduce"] == 0) == (n == 1)
+
+    check()
