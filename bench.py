@@ -168,23 +168,90 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+def _config(desc, R, C, tokens_per_step, **extra):
+    """The `config` object both arms print: identical keys and values for the same workload."""
+    cfg = {"workload": desc, "R": R, "C": C, "tokens_per_step": tokens_per_step, "layers": NL, "embed_dim": D, "heads": H,
+           "weights": "random-init (reference recipe model.py:89-101, seed 42)"}
+    cfg.update(extra)
+    return cfg
+
+
+class CpuReference:
+    """The CPU arm: the reference's OWN ``modules.AxialTransformerLayer`` (staged unmodified in oracle/_ref by
+    oracle/build_ref.py; shipped chunking ``max_tokens_per_msa=16384``, i.e. its real ``_batched_forward`` path,
+    modules.py:717-750 / 849-873) on all host cores; the oracle port only if the staged files are missing.
+    One sample = embedding (oracle restatement of model.py:346-367; < 1 % of the time) + ONE layer at the full shape
+    with ``need_head_weights=True`` as model.py:379-383 calls it; the column probabilities are dropped per layer
+    (the unmodified model keeps 10 x [12,C,1,R,R] fp32 alive: 32 GiB at cfg2)."""
+
+    def __init__(self, R, C, embed_positions_msa, threads=None):
+        import torch
+        from oracle import msa_ref as O
+        from oracle import build_ref
+        self.torch, self.O = torch, O
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core (count reported in the JSON)
+        torch.set_num_threads(threads or os.cpu_count() or 1)
+        self.threads = torch.get_num_threads()
+        self.R, self.C = R, C
+        self.sd = O.make_weights(42, num_layers=1, embed_positions_msa=embed_positions_msa)
+        self.tokens = O.make_tokens(R, C, 0)
+        self.kind = "port"
+        self.layer = None
+        if build_ref.available():
+            ref_modules, _ = build_ref.import_reference()
+            layer = ref_modules.AxialTransformerLayer(D, F, H, 0.1, 0.1, 0.1, max_tokens_per_msa=2 ** 14)
+            own = {k[len("layers.0."):]: v for k, v in self.sd.items() if k.startswith("layers.0.")}
+            layer.load_state_dict(own, strict=True)
+            self.layer = layer.eval()
+            self.kind = "reference"
+
+    def describe(self):
+        what = ("the reference's own modules.AxialTransformerLayer (oracle/_ref, unmodified, max_tokens_per_msa=16384: "
+                "its chunked _batched_forward path)" if self.kind == "reference"
+                else "oracle port of the reference fp32 CPU forward (oracle/_ref not staged)")
+        return f"embedding + ONE of {NL} AxialTransformerLayers at the full {self.R}x{self.C} shape per step: {what}"
+
+    def one_layer(self, x, pm):
+        if self.layer is not None:
+            y, col_attn, row_attn = self.layer(x, self_attn_padding_mask=pm, need_head_weights=True)
+            del col_attn
+            return y, row_attn
+        y, _, rp = self.O.axial_layer(self.sd, 0, x, pm)
+        return y, rp
+
+    def sample(self):
+        """-> (seconds embedding, seconds one layer)."""
+        torch = self.torch
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            x, pm = self.O.embed(self.sd, self.tokens)
+            x = x.permute(1, 2, 0, 3).contiguous()
+            t1 = time.perf_counter()
+            self.one_layer(x, pm)
+            t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    def full_forward(self):
+        """One REAL forward: embedding + all 10 layers (same layer object: every layer of the random-init model has
+        the same shapes and cost) + final LayerNorm, streaming the maps.  -> seconds."""
+        torch = self.torch
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            x, pm = self.O.embed(self.sd, self.tokens)
+            x = x.permute(1, 2, 0, 3).contiguous()
+            maps = []
+            for _ in range(NL):
+                x, rp = self.one_layer(x, pm)
+                maps.append(rp)
+            x = self.O.layer_norm(x, self.sd["emb_layer_norm_after.weight"], self.sd["emb_layer_norm_after.bias"])
+            return time.perf_counter() - t0
+
+
 def cpu_reference_sample(R, C, embed_positions_msa, threads=None):
-    """One AxialTransformerLayer of the CPU oracle (port of modules.py:242-267) at the full R x C
-    shape + the embedding, fp32, all host threads.  Returns (seconds for the sample, threads)."""
-    import torch
-    from oracle import msa_ref as O
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core (count reported in the JSON)
-    torch.set_num_threads(threads or os.cpu_count() or 1)
-    sd = O.make_weights(42, num_layers=1, embed_positions_msa=embed_positions_msa)
-    tokens = O.make_tokens(R, C, 0)
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        x, pm = O.embed(sd, tokens)
-        x = x.permute(1, 2, 0, 3)
-        t1 = time.perf_counter()
-        x, _, rp = O.axial_layer(sd, 0, x, pm)
-        t2 = time.perf_counter()
-    return (t1 - t0), (t2 - t1), torch.get_num_threads()
+    """(seconds embedding, seconds one layer, threads, kind, description) of one CPU sample."""
+    ref = CpuReference(R, C, embed_positions_msa, threads)
+    t_emb, t_layer = ref.sample()
+    return t_emb, t_layer, ref.threads, ref.kind, ref.describe()
 
 
 def run_reference(args):
@@ -196,26 +263,238 @@ def run_reference(args):
         lens = cfg3_lengths()
         C = sorted(lens)[len(lens) // 2]
     tokens = R * C
-    times = []
-    threads = os.cpu_count()
+    ref = CpuReference(R, C, epm)
+    samples, fwd = [], []
     for i in range(args.warmup + args.steps):
-        t_emb, t_layer, threads = cpu_reference_sample(R, C, epm)
+        t_emb, t_layer = ref.sample()
         if i >= args.warmup:
-            times.append(t_emb + NL * t_layer)          # one layer timed, x10 layers extrapolated
-    per_fwd = sum(times) / len(times)
+            samples.append(t_emb + t_layer)
+            fwd.append(t_emb + NL * t_layer)            # one layer timed; the other nine are identical in shape and cost
+    per_sample = sum(samples) / len(samples)
+    per_fwd = sum(fwd) / len(fwd)
     value = tokens / per_fwd
-    sample = (f"oracle port of the reference fp32 CPU forward: embedding + ONE of {NL} AxialTransformerLayers at the "
-              f"full {R}x{C} shape per step, extrapolated x{NL}")
+    full = None
+    if per_fwd < float(os.environ.get("RNAMSM_REF_FULL_FORWARD_MAX_S", "150")):
+        t_full = ref.full_forward()                     # one real 10-layer forward, to check the extrapolation
+        full = {"ms": t_full * 1e3, "tokens_per_s": tokens / t_full, "layers": NL}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_fwd * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_sample * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "R": R, "C": C, "tokens_per_step": tokens, "layers": NL},
-        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": _config(desc, R, C, tokens, batch_tokens=None, tokens_per_step_scope="one MSA per step",
+                          precision="fp32 torch CPU (the reference's own arithmetic)",
+                          parallelism=f"{ref.threads} host threads, one process", l2="n/a (CPU)"),
+        "extrapolated_from_layers": 1,
+        "ms_per_forward_extrapolated": per_fwd * 1e3,
+        "full_forward_measured": full,
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": ref.threads, "kind": ref.kind,
+                         "sample": ref.describe() + f"; value = tokens / (t_emb + {NL} x t_layer)"},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def _rel_err(a, b):
+    """max|a - b| / max|b| (the norm-relative gate of SURVEY.md 8d)."""
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def run_secondary(args, pkg, _lib, world, rank, peaks):
+    """The other BASELINE configs in the same run, so that the driver's records carry them (rank 0 returns the dict).
+
+    N = 1 : cfg5 (1024x1024), cfg4 (4096x128), cfg1 (512x36) single-GPU forwards, a few steps each: ms, tokens/s, e2e,
+            per-class TF/s incl. the tied row attention's fraction of the measured bf16 peak; cfg2 in the fp32 path.
+    N > 1 : cfg5 and cfg4 as ONE MSA sharded over the N ranks (fused peer-memory schedule): device ms (max over
+            ranks), e2e ms (host tokens in, every rank's map rows + rank 0's emb back in host memory), against the
+            single-GPU forward of the same MSA timed on rank 0 in the same run -> speed-up; plus `parity`: the sharded
+            result against the single-GPU forward on a small padded MSA (max over ranks of the norm-relative error).
+    All ranks must call this together."""
+    import torch
+    import torch.distributed as dist
+    from rnamsm_b200.sharded import ShardedHostOutput, sharded_forward
+
+    vocab = pkg.Vocab(pkg.Alphabet())
+    steps = 3
+    out = {}
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_model(epm, precision="fp16"):
+        torch.manual_seed(42)
+        return pkg.MSATransformer(vocab, num_layers=NL, embed_positions_msa=epm, precision=precision).eval().cuda()
+
+    def time_events(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def time_wall(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / n
+
+    def single_gpu(model, R, C, n_steps, with_classes):
+        """device ms, e2e ms (+ per-class TF/s) of the one-GPU forward of a synthetic R x C MSA."""
+        tok_host = synthetic_tokens(R, C, seed=100).pin_memory()
+        tok_dev = tok_host.cuda()
+        emb_host = torch.empty((C - 1, D), dtype=torch.float32).pin_memory()
+        atp_host = torch.empty((NL * H, C - 1, C - 1), dtype=torch.float32).pin_memory()
+        fwd = lambda: model(tok_dev, repr_layers=[NL], need_head_weights=True, want_logits=False)
+        ms = time_events(fwd, n_steps, 2)
+        res = {"ms_per_step": round(ms, 3), "tokens_per_s": round(R * C / (ms * 1e-3), 1),
+               "whole_forward_tflops": round(total_flops(R, C) / (ms * 1e-3) / 1e12, 1)}
+        e2e = time_wall(lambda: pkg.extract_features_streamed(model, tok_host, atp_host, emb_host), n_steps, 1)
+        res["e2e_ms_per_step"] = round(e2e, 3)
+        res["e2e_tokens_per_s"] = round(R * C / (e2e * 1e-3), 1)
+        if with_classes:
+            _lib.profile_enable(True)
+            for _ in range(n_steps):
+                fwd()
+            torch.cuda.synchronize()
+            prof = _lib.profile_collect()
+            _lib.profile_enable(False)
+            fl = flops_breakdown(R, C)
+            res["class_tflops"] = {k: round(fl[k] * n_steps / (prof[k][0] * 1e-3) / 1e12, 1) for k in fl if prof[k][0] > 0}
+            tot = sum(v[0] for v in prof.values())
+            res["class_time_share"] = {k: round(v[0] / tot, 4) for k, v in prof.items() if v[1]}
+            t_tied = prof["row_logits"][0] + prof["row_av"][0]
+            tied = (fl["row_logits"] + fl["row_av"]) * n_steps / (t_tied * 1e-3) / 1e12
+            tied_sm = (fl["row_logits"] + fl["row_av"]) * n_steps / ((t_tied + prof["row_softmax"][0]) * 1e-3) / 1e12
+            res["tied_row_attention"] = {
+                "tflops": round(tied, 1), "frac_of_bf16_sustained": round(tied / peaks["bf16_sustained"], 4),
+                "frac_of_bf16_burst": round(tied / peaks["bf16_burst"], 4),
+                "tflops_incl_softmax_pass": round(tied_sm, 1),
+                "what": "tied logits (umma_gemm_kernel<TIED>) + AV (umma_gemm_kernel<AV>): 4 R C^2 D flops per layer over "
+                        "their live CUDA-event time inside the forward"}
+        del tok_dev, atp_host, emb_host
+        return res
+
+    big = (("cfg5", 1024, 1024, True), ("cfg4", 4096, 128, False))
+    if world == 1:
+        models = {}
+        for name, R, C, epm in big + (("cfg1", 512, 36, True),):
+            if epm not in models:
+                models[epm] = make_model(epm)
+            out[name] = {"workload": WORKLOADS[name][3], "R": R, "C": C,
+                         **single_gpu(models[epm], R, C, steps if name != "cfg1" else 10, True)}
+            torch.cuda.empty_cache()
+        models.clear()
+        torch.cuda.empty_cache()
+        try:                                            # BASELINE configs[1] also names the fp32 path
+            m32 = make_model(True, "fp32")
+            R, C = 512, 256
+            tok = synthetic_tokens(R, C, seed=100).cuda()
+            ms = time_events(lambda: m32(tok, repr_layers=[NL], need_head_weights=True, want_logits=False), 2, 1)
+            out["cfg2_fp32"] = {"workload": WORKLOADS["cfg2"][3] + ", fp32 path", "ms_per_step": round(ms, 2),
+                                "tokens_per_s": round(R * C / (ms * 1e-3), 1),
+                                "whole_forward_tflops": round(total_flops(R, C) / (ms * 1e-3) / 1e12, 1)}
+            del m32
+        except Exception as e:                          # never lose the main line to a secondary measurement
+            out["cfg2_fp32"] = {"error": repr(e)[:200]}
+        return out
+
+    # ---------------- N > 1: one MSA sharded over the ranks -----------------------------------------
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    models = {}
+    for name, R, C, epm in big:
+        entry = {"workload": WORKLOADS[name][3], "R": R, "C": C, "n_gpus": world,
+                 "parallelism": "rows (tied row attention, P2P logit reduce-scatter + softmax + all-gather) <-> columns "
+                                "(column attention, LayerNorm push / out-projection scatter), peer-memory kernels over "
+                                "NVLink, flag barriers in peer memory"}
+        try:
+            if R % world or C % world or (C // world) % 16:
+                raise ValueError(f"{R}x{C} does not split over {world} ranks")
+            if epm not in models:
+                models[epm] = make_model(epm)
+            model = models[epm]
+            single = single_gpu(model, R, C, 2, False) if rank == 0 else None      # same box, same run, rank 0 alone
+            torch.cuda.empty_cache()
+            sync_all()
+            tok_host = synthetic_tokens(R, C, seed=100).pin_memory()
+            tok_dev = tok_host.cuda()
+            host = ShardedHostOutput(NL, H, C, D, start=1)
+            dev_fn = lambda: sharded_forward(model, tok_dev, fused=True, gather_maps=False)
+            for _ in range(2):
+                dev_fn()
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                dev_fn()
+            e1.record()
+            sync_all()
+            ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+            e2e_fn = lambda: sharded_forward(model, tok_host.cuda(non_blocking=True), fused=True, host_out=host,
+                                             gather_maps=False)
+            e2e_fn()
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_fn()
+            sync_all()
+            e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+            host.close()
+            if rank == 0:
+                entry.update({
+                    "single_gpu_ms": single["ms_per_step"], "single_gpu_e2e_ms": single["e2e_ms_per_step"],
+                    "sharded_ms": round(ms, 3), "sharded_e2e_ms": round(e2e, 3),
+                    "speedup": round(single["ms_per_step"] / ms, 3), "e2e_speedup": round(single["e2e_ms_per_step"] / e2e, 3),
+                    "tokens_per_s": round(R * C / (ms * 1e-3), 1), "e2e_tokens_per_s": round(R * C / (e2e * 1e-3), 1),
+                    "whole_forward_tflops_per_gpu": round(total_flops(R, C) / world / (ms * 1e-3) / 1e12, 1),
+                    "steps": steps, "d2h_bytes_per_step_all_ranks": (NL * H * (C - 1) ** 2 + (C - 1) * D) * 4})
+            del tok_dev, host
+            torch.cuda.empty_cache()
+        except Exception as e:
+            entry["error"] = repr(e)[:300]
+        out[name] = entry
+    # ---- multi-rank parity: the sharded forward against the one-GPU forward of the same model, small padded MSA ----
+    try:
+        Rp, Cp = 64, 128
+        model = models.get(True) or make_model(True)
+        tok = synthetic_tokens(Rp, Cp, seed=7)
+        tok[:, -2:, 1:] = vocab.pad_idx                 # two all-pad rows
+        tok[:, :, -3:] = vocab.pad_idx                  # three pad columns (masked keys, zeroed queries)
+        tok = tok.cuda()
+        ref = model(tok, repr_layers=[NL], need_head_weights=True, want_logits=False)
+        got = sharded_forward(model, tok, fused=True, gather_maps=True)
+        r0, r1 = got["row_shard"]
+        e_rep = _rel_err(got["representations"][NL], ref["representations"][NL][:, r0:r1])
+        e_map = _rel_err(got["row_attentions"], ref["row_attentions"])
+        got_n = sharded_forward(model, tok, fused=False, gather_rows=True)
+        e_rep_n = _rel_err(got_n["representations"][NL], ref["representations"][NL])
+        e_map_n = _rel_err(got_n["row_attentions"], ref["row_attentions"])
+        errs = [max_over_ranks(v) for v in (e_rep, e_map, e_rep_n, e_map_n)]
+        out["parity"] = {"shape": [Rp, Cp], "pad_rows": 2, "pad_cols": 3, "layers": NL, "n_gpus": world,
+                         "fused_emb_err": errs[0], "fused_map_err": errs[1], "nccl_emb_err": errs[2], "nccl_map_err": errs[3],
+                         "parity_err": max(errs), "gate": 3e-3, "ok": max(errs) < 3e-3,
+                         "what": "max over ranks of max|sharded - single GPU| / max|single GPU| on representations[10] "
+                                 "(each rank's row shard) and on the 120 maps; fp16 path (the re-laid-out tensors are "
+                                 "rounded to 16 bits once more, hence not bit-equal)"}
+    except Exception as e:
+        out["parity"] = {"error": repr(e)[:300]}
+    sync_all()
+    return out if rank == 0 else None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -262,10 +541,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     shard = bool(args.shard) and world > 1
+    # the other BASELINE configs, measured in the same run (cfg5 / cfg4: single GPU at N = 1, ONE MSA sharded over the
+    # ranks at N > 1, with a multi-rank parity number) -- see run_secondary
+    want_secondary = args.workload == "cfg2" and not args.shard and not args.no_secondary and args.precision == "fp16"
+    shard_host = None
     if shard:
-        from rnamsm_b200.sharded import sharded_forward
+        from rnamsm_b200.sharded import ShardedHostOutput, sharded_forward
         tok_host = synthetic_tokens(R, C, seed=100).pin_memory()   # the SAME MSA on every rank
         tok_dev = tok_host.cuda()
+        if args.fused:                                             # host results: shared atp buffer + rank 0's emb
+            shard_host = ShardedHostOutput(NL, H, C, D, start=1)
 
     if farm:
         farm_host = [synthetic_tokens(R, c, seed=200 + i).pin_memory() for i, c in zip(mine, my_C)]
@@ -276,7 +561,7 @@ def run_ours(args):
 
     def step_device():
         if shard:
-            return sharded_forward(model, tok_dev, fused=args.fused)
+            return sharded_forward(model, tok_dev, fused=args.fused, gather_maps=not args.fused)
         if farm:
             out = None
             if groups is not None:
@@ -305,8 +590,12 @@ def run_ours(args):
                 pkg.extract_features_streamed(model, th, atp_host.view(-1)[:NL * H * (c - 1) ** 2].view(NL * H, c - 1, c - 1),
                                               emb_host.view(-1)[:(c - 1) * D].view(c - 1, D))
             return
+        if shard and args.fused:
+            # every rank DMAs the map rows it owns into the shared host buffer over its own PCIe link, rank 0 its emb
+            sharded_forward(model, tok_host.cuda(non_blocking=True), fused=True, host_out=shard_host, gather_maps=False)
+            return
         if shard:
-            out = sharded_forward(model, tok_host.cuda(non_blocking=True), fused=args.fused)
+            out = sharded_forward(model, tok_host.cuda(non_blocking=True), fused=False)
             if rank == 0:                                           # rank 0 owns MSA row 0 and writes the files
                 att = out["row_attentions"][..., 1:, 1:].reshape(-1, C - 1, C - 1)
                 atp_host.copy_(att, non_blocking=True)
@@ -402,35 +691,29 @@ def run_ours(args):
                                                   * args.steps / (ms_total * 1e-3) / 1e12, 2),
         }
         cpu = None
-        if world == 1:                                  # contract: the CPU baseline is timed at N=1 only
-            if farm:                                    # bounded sample: the median-length MSA of the batch
-                c_med = sorted(lens)[len(lens) // 2]
-                t_emb, t_layer, threads = cpu_reference_sample(R, c_med, epm)
-                tokens_per_step_cpu = R * c_med
-            else:
-                t_emb, t_layer, threads = cpu_reference_sample(R, C, epm)
-                tokens_per_step_cpu = tokens_per_step
+        if world == 1 and not args.no_cpu_baseline:     # contract: the CPU baseline is timed at N=1 only
+            c_cpu = sorted(lens)[len(lens) // 2] if farm else C   # cfg3: bounded sample = the median-length MSA
+            t_emb, t_layer, threads, kind, what = cpu_reference_sample(R, c_cpu, epm)
             per_fwd = t_emb + NL * t_layer
-            cpu = {"value": tokens_per_step_cpu / per_fwd, "unit": "tokens/s", "cores": threads, "kind": "port",
-                   "sample": f"embedding + ONE of {NL} AxialTransformerLayers of the oracle (fp32 torch CPU port of "
-                             f"modules.py:242-267) at the full {R}x{c_med if farm else C} shape = {t_emb + t_layer:.1f} s, x{NL} layers"}
+            cpu = {"value": R * c_cpu / per_fwd, "unit": "tokens/s", "cores": threads, "kind": kind,
+                   "sample": f"{what} = {t_emb + t_layer:.1f} s measured; value = tokens / (t_emb + {NL} x t_layer)"}
+        secondary = run_secondary(args, pkg, _lib, world, rank, peaks) if want_secondary else None
         line = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if shard else "weak",
             "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "bf16_pure": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": desc, "R": R, "C": C, "tokens_per_step_per_gpu": tokens_per_step, "layers": NL,
-                       "batch_tokens": (args.batch_tokens if farm else None),
-                       "embed_dim": D, "heads": H, "weights": "random-init (reference recipe model.py:89-101, seed 42)",
-                       "precision": f"{args.precision}: 16-bit operands on tcgen05 (kind::f16), fp32 accumulate / residual "
-                                    "stream / LayerNorm / softmax / exported maps" if args.precision != "fp32"
-                                    else "fp32 FFMA parity path",
-                       "parallelism": (f"one MSA sharded over {world} GPUs: rows (tied row attention, fp32 logit all-reduce) "
-                                       f"<-> columns (column attention, 16-bit all-to-all), "
-                                       + ("fused peer-memory kernels over NVLink" if args.fused else "NCCL over NVLink")) if shard
-                                      else f"dp{world} independent MSAs, no collective",
-                       "l2": "no explicit flush: per-step working set (>= 1.4 GB activations + 183 MB weights at "
-                             "cfg2) exceeds the 126 MB L2"},
+            "config": _config(desc, R, C, tokens_per_step, batch_tokens=(args.batch_tokens if farm else None),
+                              tokens_per_step_scope="whole job" if (shard or farm) else "per GPU (x n_gpus independent MSAs)",
+                              precision=f"{args.precision}: 16-bit operands on tcgen05 (kind::f16), fp32 accumulate / residual "
+                                        "stream / LayerNorm / softmax / exported maps" if args.precision != "fp32"
+                                        else "fp32 FFMA parity path",
+                              parallelism=(f"one MSA sharded over {world} GPUs: rows (tied row attention, fp32 logit exchange) "
+                                           f"<-> columns (column attention, 16-bit re-layout), "
+                                           + ("fused peer-memory kernels over NVLink" if args.fused else "NCCL over NVLink")) if shard
+                                          else f"dp{world} independent MSAs, no collective",
+                              l2="no explicit flush: per-step working set (>= 1.4 GB activations + 183 MB weights at "
+                                 "cfg2) exceeds the 126 MB L2"),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": (sum(t.numel() for t in farm_host) if farm else tok_host.numel()) * 8,
                     "d2h_bytes_per_step": (sum(NL * H * (c - 1) ** 2 + (c - 1) * D for c in my_C) if farm
@@ -439,8 +722,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
+    elif want_secondary:
+        run_secondary(args, pkg, _lib, world, rank, measured_peaks())
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -457,6 +743,10 @@ def main():
     ap.add_argument("--batch-tokens", type=int, default=0,
                     help="cfg3 only: group the MSAs into forward_batch passes of at most this many tokens "
                          "(0 = one forward per MSA, the reference's B=1 loop)")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the `secondary` block (cfg5 / cfg4 / cfg1 / fp32 at N = 1; the sharded single-MSA forward "
+                         "with its parity check at N > 1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline sample (development runs)")
     ap.add_argument("--shard", action="store_true",
                     help="N > 1: ONE deep MSA sharded over the ranks (rows for tied row attention, columns for column "
                          "attention; NCCL all-reduce + all-to-all) -> strong scaling.  Default: independent MSAs, weak.")

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RNAMSM_ABI_VERSION 2
+#define RNAMSM_ABI_VERSION 3
 
 enum { RNAMSM_F32 = 0, RNAMSM_BF16 = 1, RNAMSM_F16 = 2 };
 #define RNAMSM_MAX_PEERS 8 /* GPUs of one NVSwitch box a single MSA can be sharded over */
@@ -282,12 +282,29 @@ int rnamsm_layernorm_push(const float* x, const float* w, const float* b, void* 
 
 /* Tied-logit exchange fused with K5: rank `rank` owns query rows [rank*C/n, (rank+1)*C/n); it pulls
  * those rows of every rank's partial logits (peer_partial[g]: fp32 [n_splits, H, C, C]), sums them,
- * applies logit_scale / key mask / softmax, writes the fp32 map rows into map_rank0 (a pointer into rank
- * 0's [H, C, C] map, or NULL) and the 16-bit probabilities into every rank's peer_probs[g] [H, C, ld_lp].
- * Replaces all-reduce + rnamsm_row_softmax. */
+ * applies logit_scale / key mask / softmax, writes the fp32 map rows it owns into map_out (THIS rank's
+ * [H, C, C] map slab of the layer, or NULL; rows of other owners are left untouched) and the 16-bit
+ * probabilities into every rank's peer_probs[g] [H, C, ld_lp].  Replaces all-reduce + rnamsm_row_softmax. */
 int rnamsm_row_softmax_p2p(void* const* peer_partial, int n_ranks, int rank, int n_splits, int H, int C,
-                           const uint8_t* key_pad, float logit_scale, float* map_rank0, void* const* peer_probs,
+                           const uint8_t* key_pad, float logit_scale, float* map_out, void* const* peer_probs,
                            int ld_lp, int dtype, void* stream);
+
+/* Stream-ordered barrier across the ranks in peer memory (no NCCL call): peer_flags[g] is rank g's flag array
+ * (>= n_ranks uint32, zero-initialised by rnamsm_peer_alloc).  `epoch` must be the same on every rank and grow by
+ * one per barrier.  Work enqueued after it on `stream` starts once every rank's stream has reached its own call;
+ * all peer writes of kernels enqueued before it are visible.  A peer that never arrives traps after ~10 s. */
+int rnamsm_peer_barrier(void* const* peer_flags, int n_ranks, int rank, unsigned int epoch, void* stream);
+
+/* Query rows [i0, i1) of one layer's maps (device, fp32 [H, C, C]) -> host_layer [H, Ls, Ls] with the first `start`
+ * rows/columns stripped (RNA_MSM_Inference.py:150-158), one pitched DMA on `stream`.  host_layer should be pinned
+ * (rnamsm_host_register) for the copy to be asynchronous. */
+int rnamsm_copy_map_rows_d2h(const float* maps_layer, int H, int C, int i0, int i1, int start, int Ls, float* host_layer,
+                             void* stream);
+
+/* Page-lock / unlock a host range in this process's CUDA context (e.g. a POSIX shared-memory mapping that all
+ * ranks of the box write their map rows into). */
+int rnamsm_host_register(void* p, size_t bytes);
+int rnamsm_host_unregister(void* p);
 
 /* Column block's out-projection fused with the column->row exchange: ctx [R*Cn, K] (this rank's column
  * shard c0..c0+Cn, token-major (r, c_local)) x W[N, K]^T + bias[N], delivered to rank r / Rn at row

@@ -74,6 +74,10 @@ SIGNATURES = {
     "rnamsm_ipc_close": (_i, [_vp]),
     "rnamsm_layernorm_push": (_i, [_vp, _vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "rnamsm_row_softmax_p2p": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _f, _vp, C.POINTER(_vp), _i, _i, _vp]),
+    "rnamsm_peer_barrier": (_i, [C.POINTER(_vp), _i, _i, C.c_uint, _vp]),
+    "rnamsm_copy_map_rows_d2h": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rnamsm_host_register": (_i, [_vp, _sz]),
+    "rnamsm_host_unregister": (_i, [_vp]),
     "rnamsm_linear_residual_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_vp), _i, _i, _i, _i, _i, _vp]),
     "rnamsm_add_layernorm": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _ll, _i, _f, _vp]),
     "rnamsm_msa_forward": (_i, [C.POINTER(ModelWeights), _vp, _i, _i, _i, _i, _vp, _vp, C.POINTER(_vp), _vp, _vp,
@@ -95,7 +99,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 assert lib.rnamsm_version() == ABI_VERSION, "librnamsm_b200.so ABI version mismatch"
 
 

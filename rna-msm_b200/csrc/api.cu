@@ -256,6 +256,8 @@ struct BatchPlan {
   size_t el;
   long long T;
   size_t off_xn, off_qkvh, off_partial, off_probs, off_map, off_pad, total;
+  size_t partial_bytes, probs_bytes;
+  std::vector<Plan> msa;      // every MSA's own plan, computed ONCE here and used by every layer
 };
 
 static int make_batch_plan(int n, const int* R, const int* C, int D, int H, int F, int dtype, BatchPlan* bp) {
@@ -269,6 +271,7 @@ static int make_batch_plan(int n, const int* R, const int* C, int D, int H, int 
       return 2;
     }
     const Plan p = make_plan(R[i], C[i], D, H, F, dtype);
+    b.msa.push_back(p);
     partial = std::max(partial, align256((size_t)p.splits * H * C[i] * C[i] * 4));
     probs = std::max(probs, align256((size_t)H * C[i] * p.ldp * p.el));
     map = std::max(map, align256((size_t)H * C[i] * C[i] * 4));
@@ -279,6 +282,7 @@ static int make_batch_plan(int n, const int* R, const int* C, int D, int H, int 
   b.off_qkvh = o;    o += align256((size_t)b.T * (size_t)std::max(4 * D, F) * b.el);
   b.off_partial = o; o += partial;
   b.off_probs = o;   o += probs;
+  b.partial_bytes = partial; b.probs_bytes = probs;
   b.off_map = o;     o += map;
   b.off_pad = o;     o += align256((size_t)b.T);
   b.total = o;
@@ -310,7 +314,9 @@ static int layer_forward_batch(const rnamsm_layer_weights* w, int D, int H, int 
   }
   long long off = 0;
   for (int i = 0; i < n; ++i) {
-    const Plan p = make_plan(R[i], C[i], D, H, F, dtype);
+    const Plan& p = bp.msa[i];
+    RNAMSM_REQUIRE((size_t)p.splits * H * C[i] * C[i] * 4 <= bp.partial_bytes && (size_t)H * C[i] * p.ldp * el <= bp.probs_bytes,
+                   "msa_forward_batch: MSA %d (splits %d) does not fit the planned partial / probs slabs", i, p.splits);
     const uint8_t* qkv_i = qkv + (size_t)off * 3 * D * el;
     const uint8_t* pad_i = (has_pad && has_pad[i]) ? pad + off : nullptr;
     float* map = (row_attn_out && row_attn_out[i])
@@ -412,6 +418,7 @@ int rnamsm_device_check(void) {
   RNAMSM_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   RNAMSM_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
   RNAMSM_REQUIRE(major == 10, "rnamsm_b200 is built for sm_100a (B200); device %d is sm_%d%d", dev, major, minor);
+  (void)gemm_max_pairs();   // resolve the CTA-pair occupancy now: every later plan and launch sees the same value
   return 0;
 }
 

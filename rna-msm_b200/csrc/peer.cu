@@ -8,14 +8,15 @@
 //                           all-to-all costs no extra pass and no NCCL call
 //   row_softmax_p2p_kernel  the tied-logit exchange: every rank owns C/n query rows, PULLS the partial
 //                           logits of those rows from all ranks (reduce-scatter), applies scale / key
-//                           mask / softmax, and PUSHES the 16-bit probabilities to all ranks and the
-//                           fp32 map to rank 0 (all-gather) -- one kernel instead of all-reduce +
+//                           mask / softmax, and PUSHES the 16-bit probabilities to all ranks (all-gather);
+//                           the fp32 map rows stay in the owner's `map_out` (every rank copies its own rows
+//                           to the host over its own PCIe link) -- one kernel instead of all-reduce +
 //                           softmax, moving (n-1)/n^2 of the logits in and the 16-bit rows out
 //   (umma_gemm.cu)          the column block's out-projection reduces its result into the ROW OWNER's
 //                           fp32 residual stream with TMA reduce-add on peer tensor maps: GEMM, the
 //                           column->row all-to-all and the residual add in one kernel
 //
-// Ordering between GPUs is the host's job (a stream-ordered tiny NCCL all-reduce between phases).
+// Ordering between GPUs: peer_barrier_kernel, a flag barrier in peer memory launched on the stream between phases.
 #include <cuda_fp16.h>
 #include <string.h>
 
@@ -86,7 +87,7 @@ layernorm_push_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 template <int kLp>
 __global__ void __launch_bounds__(128)
 row_softmax_p2p_kernel(PeerPtrs partial, int n_ranks, int rank, int n_splits, int H, int C, int i0, int i1,
-                       const uint8_t* __restrict__ key_pad, float logit_scale, float* map_rank0, PeerPtrs probs,
+                       const uint8_t* __restrict__ key_pad, float logit_scale, float* map_out, PeerPtrs probs,
                        int ld_lp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_owned = i1 - i0;
@@ -133,9 +134,9 @@ row_softmax_p2p_kernel(PeerPtrs partial, int n_ranks, int rank, int n_splits, in
   }
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  float* mdst = map_rank0 ? map_rank0 + row_off : nullptr;
+  float* mdst = map_out ? map_out + row_off : nullptr;
   const size_t lp_off = ((size_t)h * C + i) * ld_lp;
-  auto emit = [&](int j, float p) {                 // fp32 map row -> rank 0; 16-bit row -> every rank
+  auto emit = [&](int j, float p) {                 // fp32 map row -> map_out (local); 16-bit row -> every rank
     if (mdst && j < C) mdst[j] = p;
     if (j < ld_lp) {
       for (int t = 0; t < n_ranks; ++t) {
@@ -160,14 +161,14 @@ row_softmax_p2p_kernel(PeerPtrs partial, int n_ranks, int rank, int n_splits, in
 
 // Block-per-row, 128-bit version for C % 4 == 0 (every production shape): 128 threads own one (head,
 // query row), thread t holds columns 4t + 512k.  All remote float4 loads of a row are issued before
-// the first use (NVLink latency ~2 us), the fp32 map row leaves as float4 stores to rank 0, the 16-bit
+// the first use (NVLink latency ~2 us), the fp32 map row leaves as float4 stores to map_out, the 16-bit
 // row as 8-byte stores to every rank.
 constexpr int kP2pT = 8;   // C <= 512 * kP2pT
 
 template <int kLp>
 __global__ void __launch_bounds__(128)
 row_softmax_p2p_vec_kernel(PeerPtrs partial, int n_ranks, int rank, int n_splits, int H, int C, int i0, int rows_owned,
-                           const uint8_t* __restrict__ key_pad, float logit_scale, float* map_rank0, PeerPtrs probs,
+                           const uint8_t* __restrict__ key_pad, float logit_scale, float* map_out, PeerPtrs probs,
                            int ld_lp) {
   __shared__ float red[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -229,7 +230,7 @@ row_softmax_p2p_vec_kernel(PeerPtrs partial, int n_ranks, int rank, int n_splits
     const int j = 4 * tid + 512 * k;
     if (j < C) {
       const float4 p = make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
-      if (map_rank0) *reinterpret_cast<float4*>(map_rank0 + row_off + j) = p;
+      if (map_out) *reinterpret_cast<float4*>(map_out + row_off + j) = p;
       const uint2 pk = kLp == 1 ? make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w))
                                 : make_uint2(pack_f16(p.x, p.y), pack_f16(p.z, p.w));
       for (int t = 0; t < n_ranks; ++t)
@@ -239,6 +240,40 @@ row_softmax_p2p_vec_kernel(PeerPtrs partial, int n_ranks, int rank, int n_splits
         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(probs.p[(rank + t) % n_ranks]) + lp_off + j) = make_uint2(0u, 0u);
     }
   }
+}
+
+
+// -------------------------------------------------------------------------------------------
+// Cross-GPU barrier on the stream, in peer memory (replaces a host-launched 4-byte NCCL all-reduce per phase).
+// Every rank owns a flag array `flags[n]` (peer-mapped); rank r arrives by storing the barrier's epoch into
+// slot r of EVERY rank's array (st.release.sys over NVLink) and leaves once its own n slots have all reached the
+// epoch (ld.acquire.sys).  Kernels launched before it on the stream have completed (stream order), so their
+// peer writes are performed before the release; kernels after it start only once every peer has arrived.
+// Epochs only grow, so a peer that is already one barrier ahead still satisfies the wait.  The wait is bounded:
+// a rank that never arrives traps instead of hanging the box.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+peer_barrier_kernel(PeerPtrs flags, int n_ranks, int rank, unsigned epoch) {
+  const int t = threadIdx.x;
+  if (t < n_ranks) {
+    __threadfence_system();
+    unsigned* remote = reinterpret_cast<unsigned*>(flags.p[t]) + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    const unsigned* mine = reinterpret_cast<const unsigned*>(flags.p[rank]) + t;
+    unsigned v = 0;
+    long long spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      __nanosleep(200);
+      if (++spins > (1LL << 25)) {      // ~10 s
+        printf("rnamsm: peer barrier timeout (rank %d waiting for rank %d, epoch %u, saw %u)\n", rank, t, epoch, v);
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
 }
 
 }  // namespace rnamsm
@@ -309,7 +344,7 @@ int rnamsm_add_layernorm(float* x, const void* delta, int delta_dtype, const flo
 }
 
 int rnamsm_row_softmax_p2p(void* const* peer_partial, int n_ranks, int rank, int n_splits, int H, int C,
-                           const uint8_t* key_pad, float logit_scale, float* map_rank0, void* const* peer_probs,
+                           const uint8_t* key_pad, float logit_scale, float* map_out, void* const* peer_probs,
                            int ld_lp, int dtype, void* stream) {
   RNAMSM_REQUIRE(n_ranks >= 1 && n_ranks <= RNAMSM_MAX_PEERS && rank >= 0 && rank < n_ranks, "row_softmax_p2p: bad rank %d/%d", rank, n_ranks);
   RNAMSM_REQUIRE(C % n_ranks == 0, "row_softmax_p2p: C=%d must divide by %d ranks", C, n_ranks);
@@ -324,20 +359,64 @@ int rnamsm_row_softmax_p2p(void* const* peer_partial, int n_ranks, int rank, int
   if (C % 4 == 0 && C <= 512 * kP2pT && ld_lp % 4 == 0) {
     if (dtype == RNAMSM_BF16)
       row_softmax_p2p_vec_kernel<1><<<(int)rows, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, Cq, key_pad, logit_scale,
-                                                            map_rank0, pr, ld_lp);
+                                                            map_out, pr, ld_lp);
     else
       row_softmax_p2p_vec_kernel<2><<<(int)rows, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, Cq, key_pad, logit_scale,
-                                                            map_rank0, pr, ld_lp);
+                                                            map_out, pr, ld_lp);
     count_launch();
     RNAMSM_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
   if (dtype == RNAMSM_BF16)
-    row_softmax_p2p_kernel<1><<<blocks, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, i1, key_pad, logit_scale, map_rank0, pr, ld_lp);
+    row_softmax_p2p_kernel<1><<<blocks, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, i1, key_pad, logit_scale, map_out, pr, ld_lp);
   else
-    row_softmax_p2p_kernel<2><<<blocks, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, i1, key_pad, logit_scale, map_rank0, pr, ld_lp);
+    row_softmax_p2p_kernel<2><<<blocks, 128, 0, st>>>(pp, n_ranks, rank, n_splits, H, C, i0, i1, key_pad, logit_scale, map_out, pr, ld_lp);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+int rnamsm_peer_barrier(void* const* peer_flags, int n_ranks, int rank, unsigned int epoch, void* stream) {
+  RNAMSM_REQUIRE(n_ranks >= 1 && n_ranks <= RNAMSM_MAX_PEERS && rank >= 0 && rank < n_ranks, "peer_barrier: bad rank %d/%d", rank, n_ranks);
+  PeerPtrs f{};
+  for (int g = 0; g < n_ranks; ++g) {
+    RNAMSM_REQUIRE(peer_flags[g] != nullptr, "peer_barrier: null flag array for rank %d", g);
+    f.p[g] = peer_flags[g];
+  }
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, n_ranks, rank, epoch);
+  count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Query rows [i0, i1) of one layer's maps [H, C, C] (device) -> the BOS/EOS-stripped host layout [H, Ls, Ls]
+// (RNA_MSM_Inference.py:150-158: attentions[..., start:end, start:end]) in ONE pitched DMA.  Each rank of the sharded
+// forward copies only the rows it owns, over its own PCIe link, into a host buffer shared by the ranks.
+int rnamsm_copy_map_rows_d2h(const float* maps_layer, int H, int C, int i0, int i1, int start, int Ls, float* host_layer,
+                             void* stream) {
+  RNAMSM_REQUIRE(H > 0 && C > 0 && start >= 0 && Ls > 0 && start + Ls <= C, "copy_map_rows_d2h: bad shape C=%d start=%d Ls=%d", C, start, Ls);
+  const int lo = i0 > start ? i0 : start, hi = i1 < start + Ls ? i1 : start + Ls;
+  if (hi <= lo) return 0;
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  p.srcPtr = make_cudaPitchedPtr(const_cast<float*>(maps_layer), (size_t)C * 4, (size_t)C * 4, (size_t)C);
+  p.srcPos = make_cudaPos((size_t)start * 4, (size_t)lo, 0);
+  p.dstPtr = make_cudaPitchedPtr(host_layer, (size_t)Ls * 4, (size_t)Ls * 4, (size_t)Ls);
+  p.dstPos = make_cudaPos(0, (size_t)(lo - start), 0);
+  p.extent = make_cudaExtent((size_t)Ls * 4, (size_t)(hi - lo), (size_t)H);
+  p.kind = cudaMemcpyDeviceToHost;
+  RNAMSM_CHECK_CUDA(cudaMemcpy3DAsync(&p, (cudaStream_t)stream));
+  return 0;
+}
+
+int rnamsm_host_register(void* p, size_t bytes) {
+  RNAMSM_REQUIRE(p != nullptr && bytes > 0, "host_register: bad arguments");
+  RNAMSM_CHECK_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int rnamsm_host_unregister(void* p) {
+  if (p) RNAMSM_CHECK_CUDA(cudaHostUnregister(p));
   return 0;
 }
 

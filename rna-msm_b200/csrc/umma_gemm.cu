@@ -471,6 +471,29 @@ int num_sms() {
 // even number of usable SMs, so this can be below num_sms() / 2.
 int g_max_pairs = 0;
 
+// Resolved ONCE per process, before anything is planned or launched, so that every workspace plan and every launch
+// of the process sees the same value (the split count of the tied logits depends on it).  All variants of the kernel
+// have the same block size and dynamic shared memory, hence the same cluster occupancy: the DENSE instance is queried.
+static void ensure_max_pairs() {
+  if (g_max_pairs != 0) return;
+  cudaFuncSetAttribute(umma_gemm_kernel<V_DENSE, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_sms(), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, umma_gemm_kernel<V_DENSE, BLOCK_N>, &cfg);
+  if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+  const char* env = getenv("RNAMSM_GEMM_PAIRS");
+  if (env && atoi(env) > 0) n = atoi(env);
+  g_max_pairs = std::max(1, std::min(n, num_sms() / 2));
+}
+
 template <int kVariant, int kBN = BLOCK_N>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g,
                    int prof_class, cudaStream_t st, const PeerMaps* peers = nullptr) {
@@ -480,23 +503,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
                                            kSmemBytes));
     attr_set = true;
   }
-  if (g_max_pairs == 0) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(num_sms(), 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, umma_gemm_kernel<kVariant, kBN>, &cfg);
-    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
-    const char* env = getenv("RNAMSM_GEMM_PAIRS");
-    if (env && atoi(env) > 0) n = atoi(env);
-    g_max_pairs = std::min(n, num_sms() / 2);
-  }
+  ensure_max_pairs();
   const long long total = (long long)g.m_tiles * g.n_tiles * g.batches * g.splits;
   RNAMSM_REQUIRE(total > 0 && total < (1LL << 31), "umma_gemm: tile count %lld out of range", total);
   const int pairs = (int)std::min<long long>(total, g_max_pairs);
@@ -600,13 +607,14 @@ int launch_linear_16_scatter(const void* x, const void* W, const float* bias, in
   return launch_variant<V_DENSE>(ta, tb, pm.m[0], g, KC_LINEAR_OUT, st, &pm);
 }
 
-int gemm_max_pairs() { return g_max_pairs; }
+int gemm_max_pairs() { ensure_max_pairs(); return g_max_pairs; }
 
 static inline int tied_tile_n(int C) { return C <= 64 ? 64 : (C <= 128 ? 128 : BLOCK_N); }
 
 int row_logits_splits_16(int R, int C, int H) {
   const long long tiles = (long long)H * ceil_div(C, PAIR_M) * ceil_div(C, tied_tile_n(C));
-  const int pairs = g_max_pairs > 0 ? g_max_pairs : num_sms() / 2;
+  ensure_max_pairs();
+  const int pairs = g_max_pairs;
   // fewer tiles than pairs: the LARGEST split count that still fits one wave (12 head tiles x 6 splits = 72 of 74
   // pairs; rounding up to 7 would spill 10 tiles into a second, almost empty wave and double the time)
   int want = (int)std::max<long long>(1, pairs / tiles);

@@ -36,8 +36,10 @@ class ShardPlan:
             raise ValueError(f"bad world/rank {world}/{rank}")
         if R % world or C % world:
             raise ValueError(
-                f"sharded forward needs depth R={R} and columns C={C} divisible by the number of ranks {world} "
-                "(pad the MSA with <pad> rows / columns; both are masked out of every attention)")
+                f"sharded forward needs depth R={R} and columns C={C} divisible by the number of ranks {world}.  "
+                "Padding COLUMNS with <pad> is result-neutral (pad keys are masked, modules.py:780-784); padding ROWS "
+                "is NOT: align_scaling uses the padded depth (1/sqrt(R), modules.py:713-715), so the maps and "
+                "embeddings of a row-padded MSA differ from the unpadded one -- drop rows to a multiple instead")
         self.R, self.C, self.world, self.rank = R, C, world, rank
         self.Rn, self.Cn = R // world, C // world
         self.r0, self.c0 = rank * self.Rn, rank * self.Cn
@@ -252,9 +254,12 @@ _FUSED_CACHE = {}
 
 
 def sharded_forward(model, tokens: torch.Tensor, group=None, need_head_weights: bool = True,
-                    gather_rows: bool = False, fused: bool = False) -> Dict[str, object]:
+                    gather_rows: bool = False, fused: bool = False, host_out=None,
+                    gather_maps: bool = True) -> Dict[str, object]:
     """Convenience: run ``model`` (an eval-mode ``MSATransformer`` replicated on every rank's GPU) on one
-    MSA sharded over ``group``.  ``fused=True`` selects the peer-memory schedule (16-bit path)."""
+    MSA sharded over ``group``.  ``fused=True`` selects the peer-memory schedule (16-bit path); there
+    ``host_out`` (a :class:`ShardedHostOutput`) makes every rank copy the map rows it owns straight to the shared
+    host buffer and ``gather_maps=False`` skips assembling the full maps on every device."""
     L = __import__("rnamsm_b200")._lib
     L.require_cuda(tokens, "tokens")
     L.device_check(tokens.device)
@@ -263,7 +268,8 @@ def sharded_forward(model, tokens: torch.Tensor, group=None, need_head_weights: 
             key = (id(model), id(group))
             if key not in _FUSED_CACHE:
                 _FUSED_CACHE[key] = FusedShardedForward(model, group)
-            return _FUSED_CACHE[key].forward(tokens, need_head_weights=need_head_weights, pad_idx=model.vocab.pad_idx)
+            return _FUSED_CACHE[key].forward(tokens, need_head_weights=need_head_weights, pad_idx=model.vocab.pad_idx,
+                                             host_out=host_out, gather_maps=gather_maps)
         return ShardedMSAForward(CudaShardOps(model), model.num_layers, group).forward(
             tokens, need_head_weights=need_head_weights, gather_rows=gather_rows, pad_idx=model.vocab.pad_idx)
 
@@ -279,6 +285,7 @@ class PeerBuffer:
         import ctypes as C
         from . import _lib as L
         self.L, self.C = L, C
+        self.group = group
         self.nbytes = max(int(nbytes), 256)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -309,7 +316,8 @@ class PeerBuffer:
         return (self.C.c_void_p * self.world)(*[p + byte_offset for p in self.ptrs])
 
     def tensor(self, dtype: torch.dtype, shape, byte_offset: int = 0) -> torch.Tensor:
-        """This rank's own memory as a torch tensor (no copy)."""
+        """This rank's own memory as a torch tensor (no copy).  The view must not outlive the buffer: the fused
+        forward hands out CLONES of anything it returns."""
         n = 1
         for s in shape:
             n *= int(s)
@@ -325,14 +333,92 @@ class PeerBuffer:
         t._rnamsm_keepalive = (h, self)
         return t.view(dtype).view(*shape)
 
-    def close(self):
-        L = self.L
+    def close_imports(self):
         for p in self._imported:
-            L.lib.rnamsm_ipc_close(p)
+            self.L.lib.rnamsm_ipc_close(p)
         self._imported = []
+
+    def free_own(self):
         if self.own:
-            L.lib.rnamsm_peer_free(self.own)
+            self.L.lib.rnamsm_peer_free(self.own)
             self.own = None
+
+    @staticmethod
+    def close_all(bufs, group=None):
+        """Unmap every peer's memory on every rank BEFORE any owner frees it (a barrier in between)."""
+        torch.cuda.synchronize()
+        for b in bufs:
+            b.close_imports()
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.barrier(group=group)
+        for b in bufs:
+            b.free_own()
+
+
+class SharedHostBuffer:
+    """fp32 host memory visible to every rank of the box: a POSIX shared-memory file mapped by all ranks and
+    page-locked in each rank's CUDA context, so each GPU can DMA into it over its own PCIe link."""
+
+    def __init__(self, numel: int, group=None, tag: str = "maps"):
+        import mmap
+        import os
+        import uuid
+        from . import _lib as L
+        self.L = L
+        self.numel = int(numel)
+        self.nbytes = self.numel * 4
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        names = [f"/dev/shm/rnamsm_{tag}_{os.getpid()}_{uuid.uuid4().hex}" if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(names, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.path = names[0]
+        size = max(self.nbytes, mmap.PAGESIZE)
+        if rank == 0:
+            st = os.statvfs("/dev/shm")
+            if st.f_bavail * st.f_frsize < size + (64 << 20):
+                raise RuntimeError(f"/dev/shm has {st.f_bavail * st.f_frsize} bytes free, need {size}")
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_EXCL, 0o600)
+            os.ftruncate(fd, size)
+        if world > 1:
+            dist.barrier(group=group)
+        if rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, size, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        os.close(fd)
+        self.tensor = torch.frombuffer(self._mm, dtype=torch.float32, count=self.numel)
+        if rank == 0:
+            self.tensor.zero_()                   # touch every page before it is page-locked
+        if world > 1:
+            dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(self.path)                  # the mappings keep the memory alive; nothing is left behind
+        self._registered = False
+        if torch.cuda.is_available():
+            L.check(L.lib.rnamsm_host_register(self.tensor.data_ptr(), size), "host_register")
+            self._registered = True
+
+    def close(self):
+        if self._registered:
+            self.L.lib.rnamsm_host_unregister(self.tensor.data_ptr())
+            self._registered = False
+
+
+class ShardedHostOutput:
+    """Host-side results of the sharded forward, in the reference's file layouts (RNA_MSM_Inference.py:150-166):
+    ``atp`` ``[(N*H), L, L]`` fp32 in memory shared by the ranks (every rank writes the query rows it owns; complete on
+    return from ``forward``) and ``emb`` ``[L, D]`` fp32 pinned on the rank that owns MSA row 0 (rank 0)."""
+
+    def __init__(self, num_layers: int, heads: int, C: int, D: int, start: int = 1, end_strip: int = 0, group=None):
+        self.N, self.H, self.C, self.D, self.start = num_layers, heads, C, D, start
+        self.Ls = C - start - end_strip
+        self.shared = SharedHostBuffer(num_layers * heads * self.Ls * self.Ls, group, "atp")
+        self.atp = self.shared.tensor.view(num_layers * heads, self.Ls, self.Ls)
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.emb = torch.empty((self.Ls, D), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+    def close(self):
+        self.shared.close()
 
 
 class FusedShardedForward:
@@ -340,7 +426,8 @@ class FusedShardedForward:
     address peer memory over NVLink (csrc/peer.cu, umma_gemm.cu):
 
         tied logits    rnamsm_row_softmax_p2p : pull owned query rows of every rank's partial logits, softmax,
-                                                push 16-bit rows to all ranks + fp32 map rows to rank 0
+                                                push 16-bit rows to all ranks; the fp32 map rows stay with their
+                                                owner, which copies them to the host over its own PCIe link
         row -> column  rnamsm_layernorm_push  : LayerNorm rows stored straight into the column owner's
                                                 [C/n, R, D] buffer
         column -> row  rnamsm_linear_residual_scatter : out-projection GEMM whose epilogue TMA-stores the 16-bit
@@ -348,8 +435,11 @@ class FusedShardedForward:
                                                 fp32 into its residual stream); rnamsm_add_layernorm adds it
                                                 on the FFN's LayerNorm pass
 
-    Between phases: one stream-ordered 4-byte NCCL all-reduce as the cross-GPU barrier (4 per layer).
-    ``row_attentions`` is complete on rank 0 (the rank that owns MSA row 0 and writes the files)."""
+    Between phases: ``rnamsm_peer_barrier``, a flag barrier in peer memory launched on the stream (4 per layer; no
+    host-launched collective on the data path).  Results are fresh tensors (clones of the persistent peer
+    buffers): ``representations[N]`` = this rank's row shard, ``row_attentions`` = the full maps on every rank when
+    ``gather_maps`` (one NCCL all-gather of the owners' rows at the end), ``row_attentions_rows`` = the owned query
+    rows ``[N, H, C/n, C]`` otherwise."""
 
     def __init__(self, model, group=None):
         from . import _lib as L
@@ -364,22 +454,35 @@ class FusedShardedForward:
             raise ValueError("the fused peer-memory schedule exists for the 16-bit path; use ShardedMSAForward for fp32")
         self.ops = CudaShardOps(model)
         self._bufs = {}
-        self._flag = None
+        self._flags = None
+        self._epoch = [0, 0]                       # barrier epochs of the compute stream / the copy stream
+        self._side = None
         import os
         # column->row payload: 16-bit into a receive buffer (default) or fp32 TMA reduce-add straight into x
         self.scatter_fp32 = os.environ.get("RNAMSM_SCATTER_FP32", "0") == "1"
+        # RNAMSM_NCCL_BARRIER=1: the round-1 ordering (a 4-byte NCCL all-reduce per phase), kept for A/B timing
+        self.nccl_barrier = os.environ.get("RNAMSM_NCCL_BARRIER", "0") == "1"
+        self._nccl_flag = None
 
-    def _barrier(self):
-        if self.world > 1:
-            dist.all_reduce(self._flag, group=self.group)
+    def _barrier(self, which: int = 0, stream=None):
+        """Stream-ordered barrier across the ranks (flag set ``which``: 0 = compute stream, 1 = copy stream)."""
+        if self.world == 1:
+            return
+        L = self.L
+        if self.nccl_barrier and which == 0:
+            dist.all_reduce(self._nccl_flag, group=self.group)
+            return
+        self._epoch[which] += 1
+        L.check(L.lib.rnamsm_peer_barrier(self._flags.offset_array(128 * which), self.world, self.rank,
+                                          self._epoch[which], stream if stream is not None else L.stream_ptr()),
+                "peer_barrier")
 
     def _buffers(self, R, C, N):
         key = (R, C, N)
         if key in self._bufs:
             return self._bufs[key]
-        for old in self._bufs.values():
-            for b in old["all"]:
-                b.close()
+        if self._bufs:                             # a new shape: every result handed out so far was a clone
+            PeerBuffer.close_all([b for old in self._bufs.values() for b in old["all"]], self.group)
         self._bufs = {}
         L, n = self.L, self.world
         D, H = self.m.embed_dim, self.m.num_attention_heads
@@ -391,7 +494,6 @@ class FusedShardedForward:
             "xn_cols": PeerBuffer(Cn * R * D * 2, self.group),
             "partial": PeerBuffer(splits * H * C * C * 4, self.group),
             "probs": PeerBuffer(H * C * ldp * 2, self.group),
-            "maps": PeerBuffer(N * H * C * C * 4 if self.rank == 0 else 256, self.group),
             "delta": PeerBuffer(Rn * C * D * 2, self.group),
         }
         b["all"] = list(b.values())
@@ -400,8 +502,8 @@ class FusedShardedForward:
         return b
 
     @torch.no_grad()
-    def forward(self, tokens: torch.Tensor, need_head_weights: bool = True, pad_idx: int = 1) -> Dict[str, object]:
-        import ctypes as Ct
+    def forward(self, tokens: torch.Tensor, need_head_weights: bool = True, pad_idx: int = 1, host_out=None,
+                gather_maps: bool = True) -> Dict[str, object]:
         L, m, ops = self.L, self.m, self.ops
         assert tokens.ndim == 3 and tokens.shape[0] == 1, "one MSA per call: tokens [1, R, C]"
         _, R, C = tokens.shape
@@ -410,10 +512,17 @@ class FusedShardedForward:
         N, D, H = m.num_layers, m.embed_dim, m.num_attention_heads
         if Cn % 16:
             raise ValueError(f"fused schedule needs C / ranks = {Cn} to be a multiple of 16 (TMA box rows)")
+        if m.msa_position_embedding is not None and R > 1024:
+            raise RuntimeError("Using model with MSA position embedding trained on maximum MSA depth of 1024, "
+                               f"but received {R} alignments.")
         code, row_code = self.code, self.row_code
         dt, row_dt = L.torch_dtype(code), L.torch_dtype(row_code)
-        if self._flag is None:
-            self._flag = torch.zeros(1, dtype=torch.float32, device=tokens.device)
+        if self._flags is None:
+            self._flags = PeerBuffer(256, self.group)       # two sets of n uint32 flags (zeroed by peer_alloc)
+            self._nccl_flag = torch.zeros(1, dtype=torch.float32, device=tokens.device)
+            self._side = torch.cuda.Stream()
+            if n > 1:
+                dist.barrier(group=self.group)              # every rank's flag array exists and is zero
         B = self._buffers(R, C, N)
         splits, ldp = B["splits"], B["ldp"]
         x = B["x"].tensor(torch.float32, (Rn * C, D))
@@ -421,8 +530,12 @@ class FusedShardedForward:
         partial = B["partial"].tensor(torch.float32, (splits, H, C, C))
         probs = B["probs"].tensor(row_dt, (H, C, ldp))
         delta = B["delta"].tensor(dt, (Rn * C, D))
-        maps = B["maps"].tensor(torch.float32, (N, H, C, C)) if (g == 0 and need_head_weights) else None
+        want_maps = need_head_weights or host_out is not None
+        # this rank's maps: full [N, H, C, C] addressing, only the owned query rows [g*Cn, (g+1)*Cn) are ever written
+        maps = torch.empty((N, H, C, C), dtype=torch.float32, device=tokens.device) if want_maps else None
         st = L.stream_ptr()
+        main, side = torch.cuda.current_stream(), self._side
+        i0, i1 = g * Cn, (g + 1) * Cn
 
         tok = tokens[0]
         pad_full = tok.eq(pad_idx)
@@ -432,7 +545,7 @@ class FusedShardedForward:
         key_pad = CudaShardOps._u8(pad_full[0]) if has_pad else None
 
         x.copy_(ops.embed(tok[plan.rows()].contiguous(), plan.r0, R))
-        self._barrier()                                   # every rank's buffers are initialised
+        self._barrier()                                   # every rank's buffers are initialised / the previous call is over
         logit_scale = 1.0 / math.sqrt(R)
         for l in range(N):
             layer = m.layers[l]
@@ -443,12 +556,18 @@ class FusedShardedForward:
             qkv = self._linear(xn, w_qkv, b_qkv, row_code, L.EPI_BIAS, 0.125, D, pad_rows)
             L.check(L.lib.rnamsm_row_attn_logits(L.ptr(qkv), Rn, C, H, row_code, L.ptr(partial), splits, st), "row_attn_logits")
             self._barrier()                               # all partial logits written
-            map_ptr = None
-            if need_head_weights:                         # rank 0's map slab of this layer (peer pointer)
-                map_ptr = B["maps"].ptrs[0] + l * H * C * C * 4
             L.check(L.lib.rnamsm_row_softmax_p2p(B["partial"].ptr_array, n, g, splits, H, C, L.ptr(key_pad),
-                                                 float(logit_scale), map_ptr, B["probs"].ptr_array, ldp, row_code, st),
+                                                 float(logit_scale), L.ptr(maps[l]) if maps is not None else None,
+                                                 B["probs"].ptr_array, ldp, row_code, st),
                     "row_softmax_p2p")
+            if host_out is not None:                      # the owned rows of this layer's maps -> shared host memory
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    L.check(L.lib.rnamsm_copy_map_rows_d2h(L.ptr(maps[l]), H, C, i0, i1, host_out.start, host_out.Ls,
+                                                           host_out.atp[l * H].data_ptr(), side.cuda_stream),
+                            "copy_map_rows_d2h")
             self._barrier()                               # every rank's probabilities complete
             ctx = torch.empty((Rn * C, D), dtype=row_dt, device=x.device)
             L.check(L.lib.rnamsm_row_attn_av(L.ptr(probs), ldp, L.ptr(qkv), Rn, C, H, row_code, L.ptr(ctx), st), "row_attn_av")
@@ -484,12 +603,28 @@ class FusedShardedForward:
             hdn = self._linear(xn_f, w1, b1, code, L.EPI_BIAS_GELU)
             self._linear(hdn, w2, b2, code, L.EPI_BIAS_RESIDUAL, out=x)
         ops.final_ln(x, Rn * C)
-        out: Dict[str, object] = {"logits": None, "representations": {N: x.view(1, Rn, C, D)},
-                                  "row_shard": (plan.r0, plan.r0 + Rn)}
+        rep = x.view(1, Rn, C, D).clone()                 # a fresh tensor: the peer buffer is rewritten by the next call
+        out: Dict[str, object] = {"logits": None, "representations": {N: rep}, "row_shard": (plan.r0, plan.r0 + Rn)}
+        if host_out is not None:
+            if g == 0:                                    # rank 0 owns MSA row 0 = the source of *_emb.npy
+                host_out.emb.copy_(rep[0, 0, host_out.start:host_out.start + host_out.Ls], non_blocking=True)
+            with torch.cuda.stream(side):                 # returns once EVERY rank's rows have landed in host memory
+                self._barrier(1, side.cuda_stream)
+            maps.record_stream(side)
+            side.synchronize()
+            main.synchronize()
         if need_head_weights:
-            self._barrier()                               # (all ranks) the last layer's map rows have reached rank 0
-        if maps is not None:
-            out["row_attentions"] = maps.view(1, N, H, C, C)
+            rows = maps[:, :, i0:i1, :]
+            if gather_maps:
+                if n > 1:
+                    parts = [torch.empty((N, H, Cn, C), dtype=torch.float32, device=x.device) for _ in range(n)]
+                    dist.all_gather(parts, rows.contiguous(), group=self.group)
+                    out["row_attentions"] = torch.cat(parts, 2).view(1, N, H, C, C)
+                else:
+                    out["row_attentions"] = maps.view(1, N, H, C, C)
+            else:
+                out["row_attentions_rows"] = rows
+                out["row_attentions_range"] = (i0, i1)
         return out
 
 

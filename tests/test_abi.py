@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(raw, s), f"{s} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert _lib.lib.rnamsm_version() == 2
+    assert _lib.lib.rnamsm_version() == _lib.ABI_VERSION == 3
     assert _lib.lib.rnamsm_launch_count() == 0
 
 

@@ -64,6 +64,39 @@ def test_reference_arm_json_contract():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "tokens/s" and line["higher_is_better"] is True
     assert line["metric"] == bench.METRIC and line["value"] > 0 and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import build_ref
+    assert line["cpu_baseline"]["kind"] == ("reference" if build_ref.available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1
+    # the sample time is what ms_per_step reports; the x10 extrapolation has its own fields
+    assert line["extrapolated_from_layers"] == 1 and line["ms_per_forward_extrapolated"] > line["ms_per_step"]
+    assert abs(line["value"] - line["config"]["tokens_per_step"] / (line["ms_per_forward_extrapolated"] * 1e-3)) < 1e-6 * line["value"]
+    assert {"workload", "R", "C", "tokens_per_step", "layers"} <= set(line["config"])
     assert line["e2e"] == {"value": line["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_staged_reference_layer_matches_the_oracle_layer():
+    """bench's CPU arm runs the reference's own AxialTransformerLayer from oracle/_ref (staged by oracle/build_ref.py);
+    on the same weights and input it must agree with the oracle restatement to the fp32 noise floor."""
+    import pytest
+    import torch
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not staged (no reference checkout was present at build time)")
+    ref = bench.CpuReference(12, 20, True, threads=2)
+    assert ref.kind == "reference"
+    with torch.no_grad():
+        x, pm = O.embed(ref.sd, ref.tokens)
+        x = x.permute(1, 2, 0, 3).contiguous()
+        y_ref, p_ref = ref.one_layer(x, pm)
+        y_or, _, p_or = O.axial_layer(ref.sd, 0, x, pm)
+    assert O.rel_err(y_ref, y_or) < 1e-5 and O.rel_err(p_ref, p_or) < 1e-5
+    if os.path.isdir("/root/reference/msm"):
+        assert build_ref.check("/root/reference")          # staged files are byte-identical to the checkout
+
+
+def test_both_arms_print_the_same_config_keys():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count("_config(desc, R, C, tokens") >= 2     # run_reference and run_ours build `config` the same way
+    a = bench._config("w", 1, 2, 3, batch_tokens=None, tokens_per_step_scope="x", precision="p", parallelism="q", l2="r")
+    assert list(a)[:5] == ["workload", "R", "C", "tokens_per_step", "layers"]
