@@ -107,6 +107,16 @@ int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, 
  * partial: fp32 [n_splits, H, C, C].  n_splits >= 1 row ranges are summed by K5. */
 int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, float* partial, int n_splits,
                            void* stream);
+/* NormalizedResidualBlock (modules.py:385-401) in one kernel, 16-bit path: resid[M, N] (fp32, in place) += x[M, K] W[N, K]^T
+ * + bias, and y[M, N] (16-bit, y_dtype) = LayerNorm(resid) * ln_w + ln_b over the N features of each finished row --
+ * the operand of the next block's first GEMM, so no stand-alone LayerNorm pass reads the stream again.  The CTA whose
+ * TMA reduce-adds complete a 128-row block (arrivals counted in `counters`) reads the rows back from L2 and normalises.
+ * N % 128 == 0, N <= 1024.  tr_R, tr_C > 0: y row (m % tr_C) * tr_R + m / tr_C (column-major token order).
+ * counters: device int32 [2 * ceil(M / 256)], ZERO on entry; the kernel leaves them zero again (reusable as is). */
+int rnamsm_linear_residual_layernorm(const void* x, const void* W, const float* bias, long long M, int N, int K, int dtype,
+                                     float* resid, const float* ln_w, const float* ln_b, float eps, void* y, int y_dtype,
+                                     int tr_R, int tr_C, int* counters, void* stream);
+
 /* Suggested split count for K4: as many row ranges as fit ONE wave of the launch (74 CTA pairs in the
  * 16-bit path), at least 8 rows each. */
 int rnamsm_row_attn_splits(int R, int C, int H, int dtype);
@@ -218,22 +228,32 @@ typedef struct rnamsm_model_weights {
   const float* ln_before_b;
   const float* ln_after_w;
   const float* ln_after_b;
-  const float* lm_dense_w; /* [D, D] fp32 (the LM head always runs in fp32) */
+  const float* lm_dense_w; /* [D, D] fp32 (fp32 path, and the 16-bit path when lm_dense_w16 is NULL) */
   const float* lm_dense_b;
   const float* lm_ln_w;
   const float* lm_ln_b;
   const float* lm_bias;   /* [vocab] */
   const rnamsm_layer_weights* layers; /* host array, num_layers entries */
+  const void* lm_dense_w16; /* [D, D] in the call's 16-bit dtype, or NULL: the LM head's dense GEMM on the tensor cores */
 } rnamsm_model_weights;
 
 /* Bytes of scratch rnamsm_layer_forward / rnamsm_msa_forward need for an R x C MSA. */
 size_t rnamsm_workspace_bytes(int R, int C, int D, int H, int F, int dtype);
 
 /* One AxialTransformerLayer (modules.py:242-267) in place on x [R*C, D] fp32.
- * pad [R*C] uint8 or NULL.  row_probs_out [H,C,C] fp32 or NULL (then a scratch map is used). */
+ * pad [R*C] uint8 or NULL.  row_probs_out [H,C,C] fp32 or NULL (then a scratch map is used).
+ * With LayerNorm fusion enabled (RNAMSM_FUSE_LN=1, 16-bit path; off by default -- it is exact but measured slower than
+ * the stand-alone pass, see csrc/api.cu) every residual GEMM of the layer also emits the LayerNorm its successor consumes.
+ * To chain layers without any stand-alone LayerNorm: pass the NEXT layer's row-block LayerNorm as next_ln_w / next_ln_b
+ * (next_ln_dtype = that block's operand type, 0 = inherit `dtype`) -- this call's fc2 epilogue then leaves
+ * LayerNorm(x) in the workspace -- and call the next layer with xn_ready = 1 on the SAME workspace.  xn_ready = 0 and
+ * next_ln_w = NULL is the self-contained form.  rnamsm_fused_layernorm(dtype) tells whether the chain is available
+ * (16-bit dtype and RNAMSM_FUSE_LN=1); otherwise xn_ready / next_ln_* must be 0 / NULL. */
+int rnamsm_fused_layernorm(int dtype);
 int rnamsm_layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, float ln_eps, float* x, int R, int C,
                          const uint8_t* pad, int dtype, float* row_probs_out, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         size_t workspace_bytes, int xn_ready, const float* next_ln_w, const float* next_ln_b,
+                         int next_ln_dtype, void* stream);
 
 /* MSATransformer.forward (model.py:338-416) for one MSA.
  *   tokens [R,C] int64 -> x (caller-provided fp32 [R*C, D] buffer; holds the final

@@ -36,7 +36,7 @@ class ModelWeights(C.Structure):
                 ("tok_emb", _vp), ("pos_emb", _vp), ("row_pos", _vp),
                 ("ln_before_w", _vp), ("ln_before_b", _vp), ("ln_after_w", _vp), ("ln_after_b", _vp),
                 ("lm_dense_w", _vp), ("lm_dense_b", _vp), ("lm_ln_w", _vp), ("lm_ln_b", _vp), ("lm_bias", _vp),
-                ("layers", C.POINTER(LayerWeights))]
+                ("layers", C.POINTER(LayerWeights)), ("lm_dense_w16", _vp)]
 
 
 # name -> (restype, argtypes); every symbol include/rnamsm_b200.h declares
@@ -53,6 +53,7 @@ SIGNATURES = {
     "rnamsm_embed_layernorm": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "rnamsm_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _f, _i, _i, _vp]),
     "rnamsm_linear": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "rnamsm_linear_residual_layernorm": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp]),
     "rnamsm_row_attn_logits": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "rnamsm_row_attn_splits": (_i, [_i, _i, _i, _i]),
     "rnamsm_row_softmax": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _i, _i, _vp]),
@@ -66,7 +67,9 @@ SIGNATURES = {
     "rnamsm_ss_pack": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnamsm_contact_head": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rnamsm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "rnamsm_layer_forward": (_i, [C.POINTER(LayerWeights), _i, _i, _i, _f, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "rnamsm_fused_layernorm": (_i, [_i]),
+    "rnamsm_layer_forward": (_i, [C.POINTER(LayerWeights), _i, _i, _i, _f, _vp, _i, _i, _vp, _i, _vp, _vp, _sz,
+                                  _i, _vp, _vp, _i, _vp]),
     "rnamsm_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "rnamsm_peer_free": (_i, [_vp]),
     "rnamsm_ipc_export": (_i, [_vp, _vp]),

@@ -4,6 +4,7 @@
 // caller's stream against caller-owned buffers.
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <cmath>
@@ -109,11 +110,12 @@ int encode_tmap(CUtensorMap* map, int elem, const void* base, int rank, const ui
 //   partial [S, H, C, C] fp32           split-K tied logits
 //   probs   [H, C, ldp] compute dtype   softmax probabilities for the AV GEMM (16-bit paths only)
 //   map     [H, C, C]   fp32            scratch attention map when the caller does not want it
+//   cnt     [2 T / 256] int32           per (m-block, CTA rank) arrival counters of the fused residual + LayerNorm GEMM
 // ---------------------------------------------------------------------------------------------
 struct Plan {
   size_t el;  // bytes per element of the compute dtype
   int splits, ldp;
-  size_t off_xn, off_qkvh, off_partial, off_probs, off_map, total;
+  size_t off_xn, off_qkvh, off_partial, off_probs, off_map, off_cnt, total;
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -141,13 +143,15 @@ static Plan make_plan(int R, int C, int D, int H, int F, int dtype) {
   p.off_partial = o; o += align256((size_t)p.splits * H * C * C * 4);
   p.off_probs = o;   o += align256(is16(dtype) ? (size_t)H * C * p.ldp * p.el : 0);
   p.off_map = o;     o += align256((size_t)H * C * C * 4);
+  p.off_cnt = o;     o += align256(ln_counter_bytes((long long)T));   // arrival counters of the fused LayerNorm epilogue
   p.total = o;
   return p;
 }
 
 static int linear_any(const void* x, const void* W, long long M, int N, int K, int dtype, const LinearEpilogue& e,
-                      void* out, cudaStream_t st) {
-  if (is16(dtype)) return launch_linear_16(x, W, M, N, K, dtype == RNAMSM_F16, e, out, st);
+                      void* out, cudaStream_t st, const LnFuse* ln = nullptr) {
+  if (is16(dtype)) return launch_linear_16(x, W, M, N, K, dtype == RNAMSM_F16, e, out, st, ln);
+  RNAMSM_REQUIRE(ln == nullptr, "linear: LayerNorm fusion exists in the 16-bit path only");
   if (dtype == RNAMSM_F32)
     return launch_linear_f32((const float*)x, (const float*)W, M, N, K, e, (float*)out, st);
   set_error("unknown dtype %d", dtype);
@@ -160,9 +164,30 @@ static int block_dtype(int requested, int dtype) {
   return is16(requested) ? requested : dtype;
 }
 
+// RNAMSM_FUSE_LN=1 routes every LayerNorm behind a residual GEMM through that GEMM's fused epilogue (umma_gemm.cu, kLN).
+// OFF by default: the fused kernel is exact (bit-identical rows, tests/test_gpu_ops.py) but SLOWER on a B200 -- measured
+// at 131072 x 768: residual GEMM 176 us + LayerNorm 94 us = 270 us un-fused vs 804 us fused (K = 768), 598 vs 935 us
+// (K = 3072); the handshake itself is free (178 us with the row work skipped).  The 4 LayerNorm warps of a CTA keep only
+// 8 rows (24 KiB) in flight while the GEMM's own TMA traffic holds HBM at 85 % of its peak, so each dependent
+// load round trip takes ~5 us and the re-read runs at ~0.7 TB/s; hiding that latency needs ~90 KiB of rows in flight per
+// SM (Little: 2.7 TB/s x 5 us / 148), which neither the register file nor the shared memory left beside the 6-stage
+// operand ring can hold.  The stand-alone pass, with 64 warps per SM in flight, runs at 98 % of the HBM roofline.
+static bool fuse_ln_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RNAMSM_FUSE_LN");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// LayerNorm of the NEXT layer's row block, produced by this layer's fc2 epilogue (16-bit path)
+struct NextLn { const float* w; const float* b; int dtype; };
+
+// xn_ready: the workspace's xn region already holds LayerNorm_row(x) (written by the previous layer's fc2 epilogue).
 static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, float eps, float* x, int R, int C,
                          const uint8_t* pad, int dtype, float* row_probs_out, uint8_t* ws, const Plan& p,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool xn_ready = false, const NextLn* next = nullptr) {
   const long long T = (long long)R * C;
   void* xn = ws + p.off_xn;
   uint8_t* qkv = ws + p.off_qkvh;
@@ -174,8 +199,18 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   void* probs_lp = is16(row_dt) ? (void*)(ws + p.off_probs) : nullptr;
   int rc;
 
+  // With RNAMSM_FUSE_LN=1 every residual GEMM of the 16-bit path also emits the LayerNorm its successor needs
+  // (umma_gemm.cu, kLN) and the stand-alone LayerNorm passes disappear except the very first one (see fuse_ln_enabled()
+  // for why this is not the default).
+  const bool fuse = is16(dtype) && fuse_ln_enabled();
+  int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
+  // the counters are zero between launches (the kernel resets them); a layer that starts a chain zeroes them once
+  if (fuse && !xn_ready) RNAMSM_CHECK_CUDA(cudaMemsetAsync(cnt, 0, ln_counter_bytes(T), st));
+  RNAMSM_REQUIRE(!xn_ready || fuse, "layer_forward: xn_ready needs the 16-bit path with LayerNorm fusion enabled");
+  RNAMSM_REQUIRE(next == nullptr || fuse, "layer_forward: next-layer LayerNorm needs the 16-bit path with fusion enabled");
+
   // ---- tied row attention: x += out_proj(AV(softmax(sum_r q k^T)))   modules.py:385-401, 802-821
-  if ((rc = launch_layernorm(x, w->row.ln_w, w->row.ln_b, xn, row_dt, T, D, eps, st))) return rc;
+  if (!xn_ready && (rc = launch_layernorm(x, w->row.ln_w, w->row.ln_b, xn, row_dt, T, D, eps, st))) return rc;
   // align_scaling (modules.py:713-715) = 64^-1/2 / sqrt(R).  fp32 path: applied to q as the reference
   // does.  16-bit path: q carries the exact power of two 64^-1/2 and the 1/sqrt(R) factor is applied
   // to the fp32 logit sums in the softmax kernel (keeps q well inside the 16-bit normal range).
@@ -197,17 +232,18 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   } else {
     if ((rc = launch_row_av_f32(map, C, (const float*)qkv, R, C, H, (float*)ctx, st))) return rc;
   }
-  {
-    LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->row.b_out, 1.f, 0, nullptr};
-    if ((rc = linear_any(ctx, w->row.w_out, T, D, D, row_dt, e, x, st))) return rc;
-  }
-
   // ---- column attention over the MSA depth                           modules.py:875-945
   // 16-bit path: LayerNorm writes its output in column-major token order (c * R + r), so the QKV GEMM
   // produces q|k|v as [C, R, 3D] and the flash kernel's K/V boxes read rows 3D elements apart instead of
   // C * 3D (one TMA row per 2 MiB page otherwise).  ctx comes back token-major for the out-projection.
   const int col_major = is16(col_dt) && R > 1 ? 1 : 0;
-  if ((rc = launch_layernorm(x, w->col.ln_w, w->col.ln_b, xn, col_dt, T, D, eps, st, col_major ? R : 0, col_major ? C : 0)))
+  {
+    LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->row.b_out, 1.f, 0, nullptr};
+    const LnFuse ln{w->col.ln_w, w->col.ln_b, eps, xn, col_dt == RNAMSM_F16, col_major ? R : 0, col_major ? C : 0, cnt};
+    if ((rc = linear_any(ctx, w->row.w_out, T, D, D, row_dt, e, x, st, fuse ? &ln : nullptr))) return rc;
+  }
+  if (!fuse &&
+      (rc = launch_layernorm(x, w->col.ln_w, w->col.ln_b, xn, col_dt, T, D, eps, st, col_major ? R : 0, col_major ? C : 0)))
     return rc;
   if (R == 1) {
     // single-row shortcut: out_proj(v_proj(x)), modules.py:882-894.  Project with the v rows only.
@@ -225,18 +261,21 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   }
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->col.b_out, 1.f, 0, nullptr};
-    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st))) return rc;
+    const LnFuse ln{w->ffn_ln_w, w->ffn_ln_b, eps, xn, dtype == RNAMSM_F16, 0, 0, cnt};
+    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st, fuse ? &ln : nullptr))) return rc;
   }
 
   // ---- feed-forward: x += fc2(gelu(fc1(LN(x))))                        modules.py:423-427
-  if ((rc = launch_layernorm(x, w->ffn_ln_w, w->ffn_ln_b, xn, dtype, T, D, eps, st))) return rc;
+  if (!fuse && (rc = launch_layernorm(x, w->ffn_ln_w, w->ffn_ln_b, xn, dtype, T, D, eps, st))) return rc;
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_GELU, w->fc1_b, 1.f, 0, nullptr};
     if ((rc = linear_any(xn, w->fc1_w, T, F, D, dtype, e, qkv, st))) return rc;
   }
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->fc2_b, 1.f, 0, nullptr};
-    if ((rc = linear_any(qkv, w->fc2_w, T, D, F, dtype, e, x, st))) return rc;
+    LnFuse ln{nullptr, nullptr, eps, xn, 0, 0, 0, cnt};
+    if (next) { ln.w = next->w; ln.b = next->b; ln.out_fp16 = next->dtype == RNAMSM_F16; }
+    if ((rc = linear_any(qkv, w->fc2_w, T, D, F, dtype, e, x, st, next ? &ln : nullptr))) return rc;
   }
   return 0;
 }
@@ -255,7 +294,7 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
 struct BatchPlan {
   size_t el;
   long long T;
-  size_t off_xn, off_qkvh, off_partial, off_probs, off_map, off_pad, total;
+  size_t off_xn, off_qkvh, off_partial, off_probs, off_map, off_pad, off_cnt, total;
   size_t partial_bytes, probs_bytes;
   std::vector<Plan> msa;      // every MSA's own plan, computed ONCE here and used by every layer
 };
@@ -285,6 +324,7 @@ static int make_batch_plan(int n, const int* R, const int* C, int D, int H, int 
   b.partial_bytes = partial; b.probs_bytes = probs;
   b.off_map = o;     o += map;
   b.off_pad = o;     o += align256((size_t)b.T);
+  b.off_cnt = o;     o += align256(ln_counter_bytes(b.T));
   b.total = o;
   *bp = b;
   return 0;
@@ -293,7 +333,7 @@ static int make_batch_plan(int n, const int* R, const int* C, int D, int H, int 
 static int layer_forward_batch(const rnamsm_layer_weights* w, int D, int H, int F, float eps, float* x, int n,
                                const int* R, const int* C, const uint8_t* has_pad, bool any_pad, int dtype, int layer,
                                float* const* row_attn_out, uint8_t* ws, const BatchPlan& bp,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool xn_ready = false, const NextLn* next = nullptr) {
   const long long T = bp.T;
   const size_t el = bp.el;
   uint8_t* xn = ws + bp.off_xn;
@@ -306,8 +346,13 @@ static int layer_forward_batch(const rnamsm_layer_weights* w, int D, int H, int 
   const int col_dt = block_dtype(w->col.dtype, dtype);
   int rc;
 
+  // token-local LayerNorms ride on the residual GEMMs as in layer_forward; the column block's LayerNorm stays a pass
+  // per MSA because it transposes each MSA's own token order
+  const bool fuse = fuse_ln_enabled();
+  int* cnt = reinterpret_cast<int*>(ws + bp.off_cnt);
+  if (fuse && !xn_ready) RNAMSM_CHECK_CUDA(cudaMemsetAsync(cnt, 0, ln_counter_bytes(T), st));
   // ---- tied row attention (same constants as layer_forward's 16-bit branch)
-  if ((rc = launch_layernorm(x, w->row.ln_w, w->row.ln_b, xn, row_dt, T, D, eps, st))) return rc;
+  if (!(xn_ready && fuse) && (rc = launch_layernorm(x, w->row.ln_w, w->row.ln_b, xn, row_dt, T, D, eps, st))) return rc;
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS, w->row.b_qkv, 0.125f, D, any_pad ? pad : nullptr};
     if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, row_dt, e, qkv, st))) return rc;
@@ -360,18 +405,22 @@ static int layer_forward_batch(const rnamsm_layer_weights* w, int D, int H, int 
   }
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->col.b_out, 1.f, 0, nullptr};
-    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st))) return rc;
+    const LnFuse ln{w->ffn_ln_w, w->ffn_ln_b, eps, xn, dtype == RNAMSM_F16, 0, 0, cnt};
+    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st, fuse ? &ln : nullptr))) return rc;
   }
 
   // ---- feed-forward over all tokens
-  if ((rc = launch_layernorm(x, w->ffn_ln_w, w->ffn_ln_b, xn, dtype, T, D, eps, st))) return rc;
+  if (!fuse && (rc = launch_layernorm(x, w->ffn_ln_w, w->ffn_ln_b, xn, dtype, T, D, eps, st))) return rc;
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_GELU, w->fc1_b, 1.f, 0, nullptr};
     if ((rc = linear_any(xn, w->fc1_w, T, F, D, dtype, e, qkv, st))) return rc;
   }
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->fc2_b, 1.f, 0, nullptr};
-    if ((rc = linear_any(qkv, w->fc2_w, T, D, F, dtype, e, x, st))) return rc;
+    LnFuse ln{nullptr, nullptr, eps, xn, 0, 0, 0, cnt};
+    const bool emit = fuse && next != nullptr;
+    if (emit) { ln.w = next->w; ln.b = next->b; ln.out_fp16 = next->dtype == RNAMSM_F16; }
+    if ((rc = linear_any(qkv, w->fc2_w, T, D, F, dtype, e, x, st, emit ? &ln : nullptr))) return rc;
   }
   return 0;
 }
@@ -441,6 +490,16 @@ int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, 
   return linear_any(x, W, M, N, K, dtype, e, out, (cudaStream_t)stream);
 }
 
+int rnamsm_linear_residual_layernorm(const void* x, const void* W, const float* bias, long long M, int N, int K, int dtype,
+                                     float* resid, const float* ln_w, const float* ln_b, float eps, void* y, int y_dtype,
+                                     int tr_R, int tr_C, int* counters, void* stream) {
+  RNAMSM_REQUIRE(is16(dtype) && is16(y_dtype), "linear_residual_layernorm: 16-bit operands and output only (dtype %d, y %d)",
+                 dtype, y_dtype);
+  LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, bias, 1.f, 0, nullptr};
+  const LnFuse ln{ln_w, ln_b, eps, y, y_dtype == RNAMSM_F16, tr_R, tr_C, counters};
+  return launch_linear_16(x, W, M, N, K, dtype == RNAMSM_F16, e, resid, (cudaStream_t)stream, &ln);
+}
+
 int rnamsm_row_attn_splits(int R, int C, int H, int dtype) { return pick_splits(R, C, H, dtype); }
 
 int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, float* partial, int n_splits, void* stream) {
@@ -479,16 +538,20 @@ size_t rnamsm_workspace_bytes(int R, int C, int D, int H, int F, int dtype) {
   return make_plan(R, C, D, H, F, dtype).total;
 }
 
+int rnamsm_fused_layernorm(int dtype) { return (is16(dtype) && fuse_ln_enabled()) ? 1 : 0; }
+
 int rnamsm_layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, float ln_eps, float* x, int R, int C,
                          const uint8_t* pad, int dtype, float* row_probs_out, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+                         int xn_ready, const float* next_ln_w, const float* next_ln_b, int next_ln_dtype, void* stream) {
   RNAMSM_REQUIRE(D == H * 64, "layer_forward: head_dim must be 64 (D=%d H=%d)", D, H);
   RNAMSM_REQUIRE(dtype == RNAMSM_F32 || is16(dtype), "layer_forward: unknown dtype %d", dtype);
   const Plan p = make_plan(R, C, D, H, F, dtype);
   RNAMSM_REQUIRE(workspace_bytes >= p.total, "layer_forward: workspace %zu < required %zu", workspace_bytes, p.total);
   RNAMSM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "layer_forward: workspace must be 256 B aligned");
+  RNAMSM_REQUIRE((next_ln_w == nullptr) == (next_ln_b == nullptr), "layer_forward: next_ln_w and next_ln_b go together");
+  const NextLn next{next_ln_w, next_ln_b, block_dtype(next_ln_dtype, dtype)};
   return layer_forward(w, D, H, F, ln_eps, x, R, C, pad, dtype, row_probs_out, (uint8_t*)workspace, p,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, xn_ready != 0, next_ln_w ? &next : nullptr);
 }
 
 int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int R, int C, int has_pad, int dtype,
@@ -515,20 +578,40 @@ int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int
   for (int l = 0; l < N; ++l) {
     if (rep_out && rep_out[l]) RNAMSM_CHECK_CUDA(cudaMemcpyAsync(rep_out[l], x, T * D * 4, cudaMemcpyDeviceToDevice, st));
     float* map = row_attn_out ? row_attn_out + (size_t)l * H * C * C : nullptr;
-    if ((rc = layer_forward(&m->layers[l], D, H, F, m->ln_eps, x, R, C, pad_arg, dtype, map, ws, p, st))) return rc;
+    // layer l's fc2 epilogue also writes layer l+1's row-block LayerNorm (16-bit path)
+    const bool fuse = is16(dtype) && fuse_ln_enabled();
+    NextLn next{nullptr, nullptr, dtype};
+    if (fuse && l + 1 < N)
+      next = NextLn{m->layers[l + 1].row.ln_w, m->layers[l + 1].row.ln_b, block_dtype(m->layers[l + 1].row.dtype, dtype)};
+    if ((rc = layer_forward(&m->layers[l], D, H, F, m->ln_eps, x, R, C, pad_arg, dtype, map, ws, p, st, fuse && l > 0,
+                            next.w ? &next : nullptr)))
+      return rc;
   }
+  // 16-bit path with logits wanted: the LM head's dense GEMM runs on the tensor cores, so it needs the final
+  // LayerNorm's output in 16 bits as well -- written by a second (16-bit output) LayerNorm launch on the same rows
+  // before the in-place fp32 one
+  const bool lm16 = logits_out && is16(dtype) && m->lm_dense_w16 != nullptr;
+  if (lm16 && (rc = launch_layernorm(x, m->ln_after_w, m->ln_after_b, ws + p.off_xn, dtype, (long long)T, D, m->ln_eps, st)))
+    return rc;
   // emb_layer_norm_after in place (model.py:396): fp32 -> fp32, each warp reads its row before writing it
   if ((rc = launch_layernorm(x, m->ln_after_w, m->ln_after_b, x, RNAMSM_F32, (long long)T, D, m->ln_eps, st))) return rc;
   if (logits_out) {
-    // RobertaLMHead (modules.py:313-319): dense -> erf-GELU -> LayerNorm -> tied projection + bias
-    // The head is 0.6 % of the forward's flops and feeds no inference output; it runs in fp32 on
-    // the FFMA kernels in both modes (fp32 weights), reusing the q|k|v|ctx scratch region.
+    // RobertaLMHead (modules.py:313-319): dense -> erf-GELU -> LayerNorm -> tied projection + bias.
+    // 16-bit path: dense + GELU on tcgen05 (16-bit h), LayerNorm with fp32 statistics -> fp32, 12-wide tied projection in
+    // fp32.  fp32 path: FFMA throughout.  Scratch: the q|k|v|ctx region.
     uint8_t* hbuf = ws + p.off_qkvh;
     float* h32 = reinterpret_cast<float*>(hbuf + align256(T * D * 4));
     LinearEpilogue e{RNAMSM_EPI_BIAS_GELU, m->lm_dense_b, 1.f, 0, nullptr};
-    if ((rc = launch_linear_f32(x, m->lm_dense_w, (long long)T, D, D, e, (float*)hbuf, st))) return rc;
-    if ((rc = launch_layernorm((const float*)hbuf, m->lm_ln_w, m->lm_ln_b, h32, RNAMSM_F32, (long long)T, D, m->ln_eps, st)))
-      return rc;
+    if (lm16) {
+      if ((rc = launch_linear_16(ws + p.off_xn, m->lm_dense_w16, (long long)T, D, D, dtype == RNAMSM_F16, e, hbuf, st))) return rc;
+      if ((rc = launch_layernorm((const float*)hbuf, m->lm_ln_w, m->lm_ln_b, h32, RNAMSM_F32, (long long)T, D, m->ln_eps, st, 0,
+                                 0, dtype)))
+        return rc;
+    } else {
+      if ((rc = launch_linear_f32(x, m->lm_dense_w, (long long)T, D, D, e, (float*)hbuf, st))) return rc;
+      if ((rc = launch_layernorm((const float*)hbuf, m->lm_ln_w, m->lm_ln_b, h32, RNAMSM_F32, (long long)T, D, m->ln_eps, st)))
+        return rc;
+    }
     if ((rc = launch_vocab_proj(h32, m->tok_emb, m->lm_bias, (long long)T, m->vocab, D, logits_out, st))) return rc;
   }
   return 0;
@@ -565,10 +648,14 @@ int rnamsm_msa_forward_batch(const rnamsm_model_weights* m, int n_msa, const int
       return rc;
     off += (long long)R[i] * C[i];
   }
-  for (int l = 0; l < N; ++l)
+  for (int l = 0; l < N; ++l) {
+    NextLn next{nullptr, nullptr, dtype};
+    if (l + 1 < N)
+      next = NextLn{m->layers[l + 1].row.ln_w, m->layers[l + 1].row.ln_b, block_dtype(m->layers[l + 1].row.dtype, dtype)};
     if ((rc = layer_forward_batch(&m->layers[l], D, H, F, m->ln_eps, x, n_msa, R, C, has_pad, any_pad, dtype, l,
-                                  row_attn_out, ws, bp, st)))
+                                  row_attn_out, ws, bp, st, l > 0, next.w ? &next : nullptr)))
       return rc;
+  }
   return launch_layernorm(x, m->ln_after_w, m->ln_after_b, x, RNAMSM_F32, bp.T, D, m->ln_eps, st);
 }
 

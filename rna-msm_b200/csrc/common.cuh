@@ -114,6 +114,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same bound, no message: for waits inside register-tight loops (the printf call site costs live registers).
+__device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 26)) __trap();
+}
+
 // Wait used by single-thread roles (TMA producer, MMA issuer) that share a scheduler with compute
 // warps: try_wait with a suspend-time hint, so a failed probe parks the thread in hardware until the
 // phase flips (or ~16 us pass) instead of re-probing every few hundred cycles -- measured: the probe
@@ -145,6 +152,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// all state spaces: orders async-proxy accesses (TMA stores / reductions to global memory) with this thread's
+// generic-proxy accesses
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -327,6 +337,11 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const vo
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// all but the most recent kPending bulk groups of this thread have COMPLETED (writes performed)
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_pending() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
 
 // ---- UMMA descriptors ----------------------------------------------------------------------
 // Shared-memory matrix descriptor (PTX "matrix descriptor", sm_100 version field = 1).
@@ -375,6 +390,93 @@ __device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+// ---- warp-level LayerNorm ------------------------------------------------------------------------
+// A row held as nv float4 per lane (features lane*4 + i*128 ..).  Two-pass (mean, then centred variance) in
+// registers: matches nn.LayerNorm's biased variance.  ONE definition shared by the stand-alone LayerNorm kernels
+// and the GEMM's fused residual + LayerNorm epilogue, so both produce bit-identical rows.
+template <int kMaxV>
+__device__ __forceinline__ void warp_layernorm(float4 (&v)[kMaxV], int nv, int D, float eps,
+                                               const float* __restrict__ w, const float* __restrict__ b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i)
+    if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i)
+    if (i < nv) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      // explicit rounding steps: every instantiation (stand-alone kernels, GEMM epilogue) contracts the same way
+      q = __fadd_rn(q, __fadd_rn(__fmaf_rn(v[i].x, v[i].x, __fmul_rn(v[i].y, v[i].y)),
+                                 __fmaf_rn(v[i].z, v[i].z, __fmul_rn(v[i].w, v[i].w))));
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i)
+    if (i < nv) {
+      const int f = lane * 4 + i * 128;
+      const float4 ww = *reinterpret_cast<const float4*>(w + f);
+      const float4 bb = *reinterpret_cast<const float4*>(b + f);
+      v[i].x = __fmaf_rn(__fmul_rn(v[i].x, rstd), ww.x, bb.x);
+      v[i].y = __fmaf_rn(__fmul_rn(v[i].y, rstd), ww.y, bb.y);
+      v[i].z = __fmaf_rn(__fmul_rn(v[i].z, rstd), ww.z, bb.z);
+      v[i].w = __fmaf_rn(__fmul_rn(v[i].w, rstd), ww.w, bb.w);
+    }
+}
+
+// Two rows at once (their shuffle reductions interleave, so the latency of one hides behind the other); per row
+// exactly the operations of warp_layernorm, hence the same bits.
+template <int kMaxV>
+__device__ __forceinline__ void warp_layernorm2(float4 (&a)[kMaxV], float4 (&c)[kMaxV], int nv, int D, float eps,
+                                                const float* __restrict__ w, const float* __restrict__ b, int lane) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i)
+    if (i < nv) {
+      s0 += (a[i].x + a[i].y) + (a[i].z + a[i].w);
+      s1 += (c[i].x + c[i].y) + (c[i].z + c[i].w);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const float m0 = s0 / (float)D, m1 = s1 / (float)D;
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i)
+    if (i < nv) {
+      a[i].x -= m0; a[i].y -= m0; a[i].z -= m0; a[i].w -= m0;
+      c[i].x -= m1; c[i].y -= m1; c[i].z -= m1; c[i].w -= m1;
+      q0 = __fadd_rn(q0, __fadd_rn(__fmaf_rn(a[i].x, a[i].x, __fmul_rn(a[i].y, a[i].y)),
+                                   __fmaf_rn(a[i].z, a[i].z, __fmul_rn(a[i].w, a[i].w))));
+      q1 = __fadd_rn(q1, __fadd_rn(__fmaf_rn(c[i].x, c[i].x, __fmul_rn(c[i].y, c[i].y)),
+                                   __fmaf_rn(c[i].z, c[i].z, __fmul_rn(c[i].w, c[i].w))));
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+  }
+  const float r0 = rsqrtf(q0 / (float)D + eps), r1 = rsqrtf(q1 / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i)
+    if (i < nv) {
+      const int f = lane * 4 + i * 128;
+      const float4 ww = *reinterpret_cast<const float4*>(w + f);
+      const float4 bb = *reinterpret_cast<const float4*>(b + f);
+      a[i].x = __fmaf_rn(__fmul_rn(a[i].x, r0), ww.x, bb.x);
+      a[i].y = __fmaf_rn(__fmul_rn(a[i].y, r0), ww.y, bb.y);
+      a[i].z = __fmaf_rn(__fmul_rn(a[i].z, r0), ww.z, bb.z);
+      a[i].w = __fmaf_rn(__fmul_rn(a[i].w, r0), ww.w, bb.w);
+      c[i].x = __fmaf_rn(__fmul_rn(c[i].x, r1), ww.x, bb.x);
+      c[i].y = __fmaf_rn(__fmul_rn(c[i].y, r1), ww.y, bb.y);
+      c[i].z = __fmaf_rn(__fmul_rn(c[i].z, r1), ww.z, bb.z);
+      c[i].w = __fmaf_rn(__fmul_rn(c[i].w, r1), ww.w, bb.w);
+    }
 }
 
 // ---- misc math -----------------------------------------------------------------------------

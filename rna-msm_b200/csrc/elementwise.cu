@@ -11,39 +11,6 @@ namespace rnamsm {
 constexpr int kMaxVec = 8;  // D <= 8 * 128 = 1024 features per token
 
 // -------------------------------------------------------------------------------------------
-// Warp-level LayerNorm of a row held as nv float4 per lane (features lane*4 + i*128 ..).
-// Two-pass (mean, then centred variance) in registers: matches nn.LayerNorm's biased variance.
-// -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_layernorm(float4 (&v)[kMaxVec], int nv, int D, float eps,
-                                               const float* __restrict__ w, const float* __restrict__ b,
-                                               int lane) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) / (float)D;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nv) {
-      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-    }
-  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nv) {
-      const int f = lane * 4 + i * 128;
-      const float4 ww = *reinterpret_cast<const float4*>(w + f);
-      const float4 bb = *reinterpret_cast<const float4*>(b + f);
-      v[i].x = v[i].x * rstd * ww.x + bb.x;
-      v[i].y = v[i].y * rstd * ww.y + bb.y;
-      v[i].z = v[i].z * rstd * ww.z + bb.z;
-      v[i].w = v[i].w * rstd * ww.w + bb.w;
-    }
-}
-
-// -------------------------------------------------------------------------------------------
 // K1: grid (ceil(C / kColsPerBlock), R); each block first scans its row's non-pad prefix up to
 // its column range (positions = cumsum(tok != pad) * (tok != pad) + pad_idx, modules.py:286-291)
 // then one warp per token gathers E_tok[tok] + E_pos[pos] + p_row[r], LayerNorms, zeroes pads.
@@ -115,20 +82,36 @@ embed_ln_kernel(const int64_t* __restrict__ tokens, int R, int C, const float* _
 // -------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 8;
 
-// kOut: 0 = fp32, 1 = bf16, 2 = fp16
-template <int kOut>
+// kOut / kIn: 0 = fp32, 1 = bf16, 2 = fp16
+template <int kOut, int kIn = 0>
 __global__ void __launch_bounds__(kLnWarps * 32)
-layernorm_kernel(const float* x, const float* __restrict__ w, const float* __restrict__ b,
+layernorm_kernel(const void* x, const float* __restrict__ w, const float* __restrict__ b,
                  void* y, long long n_rows, int D, float eps, int tr_R, int tr_C) {  // x may alias y (in-place final LN)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / 128;
   for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < n_rows;
        row += (long long)gridDim.x * kLnWarps) {
-    const float* src = x + (size_t)row * D;
     float4 v[kMaxVec];
+    if constexpr (kIn == 0) {
+      const float* src = reinterpret_cast<const float*>(x) + (size_t)row * D;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i)
-      if (i < nv) v[i] = *reinterpret_cast<const float4*>(src + lane * 4 + i * 128);
+      for (int i = 0; i < kMaxVec; ++i)
+        if (i < nv) v[i] = *reinterpret_cast<const float4*>(src + lane * 4 + i * 128);
+    } else {
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(x) + (size_t)row * D;
+#pragma unroll
+      for (int i = 0; i < kMaxVec; ++i)
+        if (i < nv) {
+          const uint2 u = *reinterpret_cast<const uint2*>(src + lane * 4 + i * 128);
+          if constexpr (kIn == 1) {
+            v[i] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                               __uint_as_float(u.y & 0xffff0000u));
+          } else {
+            const __half2 h0 = *reinterpret_cast<const __half2*>(&u.x), h1 = *reinterpret_cast<const __half2*>(&u.y);
+            v[i] = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+          }
+        }
+    }
     warp_layernorm(v, nv, D, eps, w, b, lane);
     // optional token transpose: input row r * C + c -> output row c * R + r (column attention layout)
     const long long orow = tr_C > 0 ? (row % tr_C) * tr_R + row / tr_C : row;
@@ -291,14 +274,18 @@ int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, i
 }
 
 int launch_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
-                     float eps, cudaStream_t st, int tr_R, int tr_C) {
+                     float eps, cudaStream_t st, int tr_R, int tr_C, int x_dtype) {
   RNAMSM_REQUIRE(tr_C <= 0 || (long long)tr_R * tr_C == n_rows, "layernorm: transpose shape %d x %d != %lld rows", tr_R, tr_C, n_rows);
   RNAMSM_REQUIRE(tr_C <= 0 || (const void*)x != (const void*)y, "layernorm: the transposing form cannot run in place");
   RNAMSM_REQUIRE(D % 128 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d must be a multiple of 128 <= 1024", D);
   if (n_rows <= 0) return 0;
   const int blocks = (int)std::min<long long>((n_rows + kLnWarps - 1) / kLnWarps, 148LL * 32);
   ProfScope prof(KC_LAYERNORM, st);
-  if (y_dtype == 1)
+  if (x_dtype != 0) {   // 16-bit input -> fp32 output (the LM head's LayerNorm behind a 16-bit dense GEMM)
+    RNAMSM_REQUIRE(y_dtype == 0 && tr_C <= 0 && (x_dtype == 1 || x_dtype == 2), "layernorm: 16-bit input supports fp32 output only");
+    if (x_dtype == 1) layernorm_kernel<0, 1><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, 0, 0);
+    else layernorm_kernel<0, 2><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, 0, 0);
+  } else if (y_dtype == 1)
     layernorm_kernel<1><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
   else if (y_dtype == 2)
     layernorm_kernel<2><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);

@@ -30,7 +30,10 @@ msa_clean_kernel(const uint8_t* __restrict__ raw, const long long* __restrict__ 
   for (long long p = b; p < e; p += 32) {
     const long long q = p + lane;
     uint8_t ch = q < e ? raw[q] : (uint8_t)'.';
-    const bool keep = !((ch >= 'a' && ch <= 'z') || ch == '.' || ch == '*' || ch == '\n' || ch == '\r');
+    // Bio.SeqIO's FASTA parser (what MSA.from_fasta iterates) joins the record's lines and removes spaces, line
+    // ends and trailing blanks before from_fasta's own rules see the sequence
+    const bool keep = !((ch >= 'a' && ch <= 'z') || ch == '.' || ch == '*' || ch == '\n' || ch == '\r' || ch == ' ' ||
+                        ch == '\t');
     if (ch == 'T') ch = 'U';
     else if (ch == 'R' || ch == 'Y' || ch == 'K' || ch == 'M' || ch == 'S' || ch == 'W' || ch == 'B' || ch == 'D' ||
              ch == 'H' || ch == 'V' || ch == 'N') ch = 'X';

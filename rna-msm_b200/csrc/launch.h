@@ -29,8 +29,9 @@ int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, i
                     int n_pos, const float* row_pos, const float* ln_w, const float* ln_b, int D, int pad_idx,
                     float eps, float* x_out, uint8_t* pad_out, cudaStream_t st);
 // tr_R, tr_C > 0: write the output in column-major token order, y[c * tr_R + r] = LN(x[r * tr_C + c])
+// x_dtype != 0: x holds 16-bit rows (1 = bf16, 2 = fp16; fp32 output only)
 int launch_layernorm(const float* x, const float* w, const float* b, void* y, int y_dtype, long long n_rows, int D,
-                     float eps, cudaStream_t st, int tr_R = 0, int tr_C = 0);
+                     float eps, cudaStream_t st, int tr_R = 0, int tr_C = 0, int x_dtype = 0);
 int launch_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float logit_scale,
                        float* probs_out, void* probs_lp, int ld_lp, int dtype, cudaStream_t st);
 int launch_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
@@ -59,9 +60,21 @@ int launch_row_logits_f32(const float* qkv, int R, int C, int H, float* partial,
 int launch_row_av_f32(const float* probs, int ldp, const float* qkv, int R, int C, int H, float* ctx, cudaStream_t st);
 int launch_col_attn_f32(const float* qkv, int R, int C, int H, const uint8_t* pad, float* ctx, cudaStream_t st);
 
+// LayerNorm fused behind a residual epilogue: y = LN(out) (full rows of N features, fp32 statistics), 16-bit.
+struct LnFuse {
+  const float* w;
+  const float* b;
+  float eps;
+  void* out;          // [M, N] 16-bit
+  int out_fp16;       // 0 = bf16, 1 = fp16
+  int tr_R, tr_C;     // > 0: output row (m % tr_C) * tr_R + m / tr_C
+  int* counters;      // >= 2 * ceil(M / 256) ints, ZERO on entry (the kernel leaves them zero again)
+};
+inline size_t ln_counter_bytes(long long M) { return (size_t)(2 * ((M + 255) / 256)) * sizeof(int); }
+
 // umma_gemm.cu -- 16-bit (bf16 / fp16 operands, fp32 accumulate) tcgen05 path; fp16 != 0 selects fp16
 int launch_linear_16(const void* x, const void* W, long long M, int N, int K, int fp16, const LinearEpilogue& epi,
-                     void* out, cudaStream_t st);
+                     void* out, cudaStream_t st, const LnFuse* ln = nullptr);
 int launch_row_logits_16(const void* qkv, int R, int C, int H, int fp16, float* partial, int n_splits, cudaStream_t st);
 int launch_row_av_16(const void* probs, int ldp, const void* qkv, int R, int C, int H, int fp16, void* ctx,
                      cudaStream_t st);

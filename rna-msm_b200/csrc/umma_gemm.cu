@@ -51,6 +51,11 @@ constexpr int kTmemCols = 512;                   // 2 accumulator stages x 256 f
 constexpr int kEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+constexpr int kLnWarps = 4;                      // LayerNorm warps of the fused residual + LayerNorm variant
+constexpr int kFirstLnWarp = kFirstEpiWarp + kEpiWarps;
+constexpr int kThreadsLn = kThreads + 32 * kLnWarps;
+constexpr int kLnMaxVec = 8;                     // N <= 8 * 128 features per row
+constexpr int kLnSlots = 4;                      // tiles the epilogue may run ahead of the LayerNorm warps
 constexpr int EPI_BUF_BYTES = 32 * 128;          // one 32-row x 128 B staging box per epilogue warp
 constexpr int kSmemBytes = kStages * STAGE_BYTES + kEpiWarps * EPI_BUF_BYTES + 256 + 1024;
 
@@ -75,6 +80,16 @@ struct GemmArgs {
   // of the fp32 residual stream of rank r / Rn, through that rank's tensor map.
   int peer_n, peer_Rn, peer_Cn, peer_c0, peer_box_rows;
   int m_tile_shift;      // DENSE: m-tile order rotated by this (per-rank) so ranks scatter to different owners at once
+  // fused residual + LayerNorm (kLN variant): y = LN(out) over full rows of N features, written in 16 bits
+  const float* ln_w;
+  const float* ln_b;
+  void* ln_out;
+  float ln_eps;
+  int ln_fp16;           // element type of ln_out: 0 = bf16, 1 = fp16
+  int ln_tr_R, ln_tr_C;  // > 0: output row (m % tr_C) * tr_R + m / tr_C (column-major token order)
+  int* ln_counters;      // [2 * m_tiles] zero on entry, zero again on exit: arrivals per (m-block, CTA rank)
+  int ln_debug;          // RNAMSM_LN_DEBUG bits (experiments): 1 skip the row work, 2 read rows half a tensor away,
+                         // 4 plain (L1-cached) loads, 8 no stores
 };
 
 struct PeerMaps { CUtensorMap m[RNAMSM_MAX_PEERS]; };
@@ -108,6 +123,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile) {
     t.split = 0; t.kb_begin = 0; t.kb_count = g.k_blocks;
   }
   return t;
+}
+
+// Persistent tile order: tile = pair + lt * n_pairs, so the n-tiles of one m-block run on neighbouring pairs at the same
+// time and share the block's A rows through L2 (giving a pair whole m-blocks instead re-reads A from HBM once its 74
+// concurrent copies outgrow L2: measured 1219 -> 944 TF/s on fc2).
+__device__ __forceinline__ int tile_at(int lt, int pair, int n_pairs, int total_tiles) {
+  const long long t = (long long)pair + (long long)lt * n_pairs;
+  return t < total_tiles ? (int)t : -1;
 }
 
 // erf-GELU for the 16-bit epilogue: erfc(z) ~= (1 + a1 z + ... + a6 z^6)^-16 (Abramowitz & Stegun
@@ -172,8 +195,8 @@ __device__ __forceinline__ void stage_row(uint8_t* buf, int lane, const uint32_t
 
 // kBN = accumulator columns of the pair tile (256; 128 / 64 for the tied logits of short alignments, where a
 // 256-wide tile would be mostly padding): each CTA stages kBN / 2 rows of B, TMEM holds 2 x kBN columns.
-template <int kVariant, int kBN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int kVariant, int kBN, bool kLN = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLN ? kThreadsLn : kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g,
                  const __grid_constant__ PeerMaps peers) {
@@ -189,7 +212,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* ln_ready = tmem_empty + 2;             // [kLnSlots] kLN: this CTA's reduce-adds of a tile have been performed
+  uint64_t* ln_free = ln_ready + kLnSlots;         // [kLnSlots] kLN: the LayerNorm warps are done with that slot
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ln_free + kLnSlots);
+  volatile int* ln_job = reinterpret_cast<volatile int*>(tmem_ptr + 1);   // [2] kLN: "this tile completed its m-block"
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -212,6 +238,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_full[a], 1);                // multicast tcgen05.commit
       mbar_init(&tmem_empty[a], 2 * kEpiWarps);   // epilogue warps of both CTAs (leader's copy is used)
     }
+    for (int a = 0; a < kLnSlots; ++a) {
+      mbar_init(&ln_ready[a], kEpiWarps);         // this CTA's epilogue warps
+      mbar_init(&ln_free[a], kLnWarps);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -229,7 +259,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      for (int lt = 0, tile; (tile = tile_at(lt, pair, n_pairs, total_tiles)) >= 0; ++lt) {
         const TileCoord t = decode_tile<kVariant, kBN>(g, tile);
         for (int kb = 0; kb < t.kb_count; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -258,7 +288,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t idesc = make_idesc_16(PAIR_M, BN, g.fp16, 0, kVariant == V_AV ? 1 : 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      for (int lt = 0, tile; (tile = tile_at(lt, pair, n_pairs, total_tiles)) >= 0; ++lt) {
         const TileCoord t = decode_tile<kVariant, kBN>(g, tile);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -287,7 +317,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= kFirstEpiWarp) {
+  } else if (warp >= kFirstEpiWarp && warp < kFirstLnWarp) {
     // ================================ epilogue (both CTAs) ========================
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
     const int half = (warp - kFirstEpiWarp) >> 2;    // accumulator columns [128*half, 128*half+128)
@@ -295,7 +325,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+    int n_local = 0;
+    auto ln_signal = [&](int i) {                    // lane 0: this warp's reduce-adds of local tile i are done
+      const int slot = i % kLnSlots, use = i / kLnSlots;
+      if (use > 0) mbar_wait(&ln_free[slot], (uint32_t)((use - 1) & 1));   // slot consumed kLnSlots tiles ago
+      mbar_arrive(&ln_ready[slot]);
+    };
+    for (int lt = 0, tile; (tile = tile_at(lt, pair, n_pairs, total_tiles)) >= 0; ++lt) {
+      n_local = lt + 1;
       const TileCoord t = decode_tile<kVariant, kBN>(g, tile);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -339,7 +376,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_wait();
           if (c == HN / 32 - 1) release_acc();
           const int n = t.n0 + half * HN + c * 32;
-          if (n >= g.N || row0 >= g.M) continue;
+          if (n >= g.N || row0 >= g.M) {
+            if (kLN && lane == 0) bulk_commit();       // an empty group: every tile commits exactly HN / 32 groups
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             const float4 b = *reinterpret_cast<const float4*>(g.bias + n + k);
@@ -369,6 +409,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             bulk_commit();
           }
+        }
+        if (kLN && lt > 0 && lane == 0) {
+          // all but this tile's HN / 32 groups are complete = the PREVIOUS tile's reduce-adds have been performed at
+          // L2 (not merely read out of the staging buffer): tell the LayerNorm warps, one tile late and without stalling
+          bulk_wait_pending<HN / 32>();
+          ln_signal(lt - 1);
         }
       } else {
         // 16-bit outputs: 64-column boxes (128 B rows), TMA store
@@ -447,7 +493,83 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) bulk_wait_all0();   // our global writes are complete before the CTA retires
+    if (lane == 0) {
+      bulk_wait_all0();                // our global writes are complete before the CTA retires
+      if (kLN && n_local > 0) ln_signal(n_local - 1);
+    }
+  } else if (kLN && warp >= kFirstLnWarp) {
+    // ================================ LayerNorm of the finished rows (both CTAs) ====
+    // An m-block's N / 256 column tiles are reduce-added into the fp32 residual stream by neighbouring pairs.  Each CTA
+    // counts its finished tiles per (m-block, CTA rank) in global memory; the CTA whose arrival completes the block
+    // ("last arriver", the threadFenceReduction pattern) owns the LayerNorm of those 128 rows: it reads them back from
+    // L2 (ld.global.cg -- they were just written there), normalises over the full N features with fp32 statistics
+    // (same code as layernorm_kernel) and writes the 16-bit operand of the next GEMM.  The stand-alone LayerNorm pass
+    // (3 KiB read + 1.5 KiB written per token from HBM) disappears.
+    const int w = warp - kFirstLnWarp;
+    const int nv = g.N >> 7;
+    const float* xs = reinterpret_cast<const float*>(g.out);
+    for (int lt = 0, tile; (tile = tile_at(lt, pair, n_pairs, total_tiles)) >= 0; ++lt) {
+      const TileCoord t = decode_tile<kVariant, kBN>(g, tile);
+      const int slot = lt % kLnSlots, use = lt / kLnSlots;
+      mbar_wait(&ln_ready[slot], (uint32_t)(use & 1));
+      if (w == 0 && lane == 0) {
+        int* cnt = g.ln_counters + 2 * (t.m0 / PAIR_M) + (int)cta_rank;
+        __threadfence();                              // our CTA's (completed) reduce-adds before the arrival
+        const int last = atomicAdd(cnt, 1) == g.n_tiles - 1;
+        if (last) {
+          *cnt = 0;                                   // nobody else touches this counter again: clean for the next launch
+          __threadfence();                            // the other CTAs' arrivals (and their rows) before our reads
+        }
+        ln_job[lt & 1] = last;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kLnWarps) : "memory");   // the LayerNorm warps only
+      if (ln_job[lt & 1] && !(g.ln_debug & 1)) {
+        fence_proxy_async_all();                      // async-proxy (TMA reduce) writes -> our generic-proxy loads
+        const int row_base = t.m0 + (int)cta_rank * BLOCK_M + w * (BLOCK_M / kLnWarps);
+#pragma unroll 1
+        for (int rr = 0; rr < BLOCK_M / kLnWarps; rr += 2) {           // two rows in flight per warp
+          const long long row = row_base + rr;
+          if (row >= g.M) break;
+          const bool two = row + 1 < g.M;
+          const long long rsrc = (g.ln_debug & 2) ? (row + g.M / 2) % (g.M - 1) : row;
+          const float* src = xs + (size_t)rsrc * g.N;
+          const float* src1 = two ? src + g.N : src;      // single tail row: read it twice, never out of bounds
+          float4 v0[kLnMaxVec], v1[kLnMaxVec];
+          if (g.ln_debug & 4) {
+#pragma unroll
+            for (int i = 0; i < kLnMaxVec; ++i)
+              if (i < nv) {
+                v0[i] = *reinterpret_cast<const float4*>(src + lane * 4 + i * 128);
+                v1[i] = *reinterpret_cast<const float4*>(src1 + lane * 4 + i * 128);
+              }
+          } else {
+#pragma unroll
+            for (int i = 0; i < kLnMaxVec; ++i)
+              if (i < nv) {
+                v0[i] = __ldcg(reinterpret_cast<const float4*>(src + lane * 4 + i * 128));
+                v1[i] = __ldcg(reinterpret_cast<const float4*>(src1 + lane * 4 + i * 128));
+              }
+          }
+          warp_layernorm2(v0, v1, nv, g.N, g.ln_eps, g.ln_w, g.ln_b, lane);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if ((q == 1 && !two) || (g.ln_debug & 8)) break;
+            const long long rw = row + q;
+            const long long orow = g.ln_tr_C > 0 ? (rw % g.ln_tr_C) * g.ln_tr_R + rw / g.ln_tr_C : rw;
+            uint16_t* dst = reinterpret_cast<uint16_t*>(g.ln_out) + (size_t)orow * g.N;
+#pragma unroll
+            for (int i = 0; i < kLnMaxVec; ++i)
+              if (i < nv) {
+                const float4 y = q == 0 ? v0[i] : v1[i];
+                *reinterpret_cast<uint2*>(dst + lane * 4 + i * 128) =
+                    make_uint2(pack16(y.x, y.y, g.ln_fp16), pack16(y.z, y.w, g.ln_fp16));
+              }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ln_free[slot]);
+    }
   }
 
   tc_fence_before();
@@ -494,12 +616,12 @@ static void ensure_max_pairs() {
   g_max_pairs = std::max(1, std::min(n, num_sms() / 2));
 }
 
-template <int kVariant, int kBN = BLOCK_N>
+template <int kVariant, int kBN = BLOCK_N, bool kLN = false>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g,
                    int prof_class, cudaStream_t st, const PeerMaps* peers = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
-    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant, kBN, kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes));
     attr_set = true;
   }
@@ -509,7 +631,8 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int pairs = (int)std::min<long long>(total, g_max_pairs);
   ProfScope prof(prof_class, st);
   static const PeerMaps no_peers{};
-  umma_gemm_kernel<kVariant, kBN><<<2 * pairs, kThreads, kSmemBytes, st>>>(ta, tb, to, g, peers ? *peers : no_peers);
+  umma_gemm_kernel<kVariant, kBN, kLN><<<2 * pairs, kLN ? kThreadsLn : kThreads, kSmemBytes, st>>>(
+      ta, tb, to, g, peers ? *peers : no_peers);
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -519,7 +642,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 
 // ---------------------------------------------------------------------------------------------
 int launch_linear_16(const void* x, const void* W, long long M, int N, int K, int fp16, const LinearEpilogue& epi,
-                     void* out, cudaStream_t st) {
+                     void* out, cudaStream_t st, const LnFuse* ln) {
   RNAMSM_REQUIRE(M > 0 && M < (1LL << 31), "linear_16: M=%lld out of range", M);
   RNAMSM_REQUIRE(N % 64 == 0 && K % BLOCK_K == 0 && K >= BLOCK_K, "linear_16: N=%d and K=%d must be multiples of 64", N, K);
   RNAMSM_REQUIRE(epi.bias != nullptr, "linear_16: bias required");
@@ -558,6 +681,23 @@ int launch_linear_16(const void* x, const void* W, long long M, int N, int K, in
   g.fp16 = fp16;
   g.epi_kind = epi.kind; g.bias = epi.bias; g.q_scale = epi.q_scale; g.q_cols = epi.q_cols; g.row_mask = epi.row_mask;
   g.out = out; g.ld_out = N;
+  if (ln != nullptr) {
+    // fused residual + LayerNorm: the CTA whose reduce-adds complete an m-block's rows reads them back from L2 and
+    // emits LayerNorm(row) as the 16-bit operand of the next GEMM (NormalizedResidualBlock, modules.py:385-401)
+    RNAMSM_REQUIRE(epi.kind == RNAMSM_EPI_BIAS_RESIDUAL, "linear_16: LayerNorm fusion needs the residual epilogue");
+    RNAMSM_REQUIRE(N % 128 == 0 && N <= 128 * kLnMaxVec, "linear_16: LayerNorm fusion needs N=%d to be a multiple of 128 <= 1024", N);
+    RNAMSM_REQUIRE(ln->w && ln->b && ln->out && ln->out != out && ln->counters,
+                   "linear_16: LayerNorm fusion needs weight, bias, a separate output and the (zeroed) arrival counters");
+    RNAMSM_REQUIRE(ln->tr_C <= 0 || (long long)ln->tr_R * ln->tr_C == M, "linear_16: LayerNorm transpose shape %d x %d != %lld rows",
+                   ln->tr_R, ln->tr_C, M);
+    g.ln_w = ln->w; g.ln_b = ln->b; g.ln_out = ln->out; g.ln_eps = ln->eps; g.ln_fp16 = ln->out_fp16;
+    g.ln_tr_R = ln->tr_R; g.ln_tr_C = ln->tr_C; g.ln_counters = ln->counters;
+    {
+      const char* e = getenv("RNAMSM_LN_DEBUG");
+      g.ln_debug = e ? atoi(e) : 0;
+    }
+    return launch_variant<V_DENSE, BLOCK_N, true>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
+  }
   return launch_variant<V_DENSE>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
 }
 

@@ -50,9 +50,6 @@ def extract_features_streamed(model: MSATransformer, tokens: torch.Tensor, atp_h
     assert tokens.ndim == 3 and tokens.shape[0] == 1
     _, R, Cc = tokens.shape
     D, H, N = model.embed_dim, model.num_attention_heads, model.num_layers
-    if model.msa_position_embedding is not None and R > 1024:
-        raise RuntimeError("Using model with MSA position embedding trained on maximum MSA depth of 1024, "
-                           f"but received {R} alignments.")
     start = int(vocab.prepend_bos)
     Ls = Cc - start - int(vocab.append_eos)
     with torch.cuda.device(dev):
@@ -62,7 +59,7 @@ def extract_features_streamed(model: MSATransformer, tokens: torch.Tensor, atp_h
         if side is None:
             side = model._copy_stream = torch.cuda.Stream()
         tok = tokens.to(dev, non_blocking=True).long().contiguous()
-        has_pad = bool(tok.eq(vocab.pad_idx).any())
+        has_pad, _ = model.check_tokens(tok)          # same limits and exceptions as forward()
         x = torch.empty((R * Cc, D), dtype=torch.float32, device=dev)
         pad = torch.empty(R * Cc, dtype=torch.uint8, device=dev)
         maps = torch.empty((N, H, Cc, Cc), dtype=torch.float32, device=dev)
@@ -73,9 +70,13 @@ def extract_features_streamed(model: MSATransformer, tokens: torch.Tensor, atp_h
         L.check(L.lib.rnamsm_embed_layernorm(L.ptr(tok[0]), R, Cc, m.tok_emb, m.vocab, m.pos_emb, m.n_pos, m.row_pos,
                                              m.ln_before_w, m.ln_before_b, D, m.pad_idx, m.ln_eps, L.ptr(x), L.ptr(pad), st),
                 "embed_layernorm")
+        chain = bool(L.lib.rnamsm_fused_layernorm(code))   # layer l's fc2 epilogue writes layer l+1's first LayerNorm
         for l in range(N):
+            nxt = m.layers[l + 1].row if (chain and l + 1 < N) else None
             L.check(L.lib.rnamsm_layer_forward(C.byref(m.layers[l]), D, H, 4 * D, m.ln_eps, L.ptr(x), R, Cc,
-                                               L.ptr(pad) if has_pad else None, code, L.ptr(maps[l]), L.ptr(ws), nbytes, st),
+                                               L.ptr(pad) if has_pad else None, code, L.ptr(maps[l]), L.ptr(ws), nbytes,
+                                               int(chain and l > 0), nxt.ln_w if nxt is not None else None,
+                                               nxt.ln_b if nxt is not None else None, nxt.dtype if nxt is not None else 0, st),
                     "layer_forward")
             ev = torch.cuda.Event()
             ev.record(main)

@@ -28,7 +28,8 @@ def split_records(path: str) -> Tuple[List[str], bytes, np.ndarray]:
     bodies: List[bytes] = []
     with open(path, "rb") as f:
         data = f.read()
-    for rec in data.split(b">")[1:]:
+    # a record starts at a '>' in the FIRST column of a line (Bio.SeqIO); a '>' inside a header ("a->b") is text
+    for rec in (b"\n" + data).split(b"\n>")[1:]:            # anything before the first record is ignored
         nl = rec.find(b"\n")
         headers.append(rec[:nl if nl >= 0 else len(rec)].decode(errors="replace").strip())
         bodies.append(rec[nl + 1:] if nl >= 0 else b"")
@@ -39,7 +40,7 @@ def split_records(path: str) -> Tuple[List[str], bytes, np.ndarray]:
 
 def cleaned_length(body: bytes) -> int:
     """Length of one record after the from_fasta rules (host: the first record only, to size the matrix)."""
-    return sum(1 for ch in body if not (97 <= ch <= 122 or ch in b".*\n\r"))
+    return sum(1 for ch in body if not (97 <= ch <= 122 or ch in b".*\n\r \t"))
 
 
 @torch.no_grad()

@@ -112,6 +112,27 @@ class MSATransformer(nn.Module, _PrecisionMixin):
     def predict_contacts(self, tokens):
         return self(tokens, return_contacts=True)["contacts"]
 
+    def check_msa_shape(self, R: int, Cc: int, n_nonpad_max: int) -> None:
+        """The reference's input limits, raised identically by every entry point (forward, forward_batch, the streamed
+        and the sharded paths): depth <= 1024 with the learned row positions (model.py:354-359) and non-pad length
+        within the learned column positions (F.embedding raises IndexError, modules.py:292)."""
+        if self.msa_position_embedding is not None and R > 1024:
+            raise RuntimeError(
+                "Using model with MSA position embedding trained on maximum MSA "
+                f"depth of 1024, but received {R} alignments.")
+        if n_nonpad_max + self.vocab.pad_idx >= self.embed_positions.weight.shape[0]:
+            raise IndexError(
+                f"sequence length {Cc} exceeds the {self.embed_positions.max_positions} learned positions")
+
+    def check_tokens(self, tokens: torch.Tensor):
+        """-> (has_pad, padding_mask) after check_msa_shape; one host sync, as model.py:347."""
+        R, Cc = tokens.shape[-2:]
+        padding_mask = tokens.eq(self.vocab.pad_idx)
+        has_pad = bool(padding_mask.any())
+        n_nonpad_max = int((~padding_mask).sum(-1).max()) if has_pad else Cc
+        self.check_msa_shape(R, Cc, n_nonpad_max)
+        return has_pad, padding_mask
+
     # -- C-ABI plumbing ------------------------------------------------------------------------
     def c_weights(self, code: int) -> L.ModelWeights:
         key = (code, self._row_code) + tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -142,6 +163,10 @@ class MSATransformer(nn.Module, _PrecisionMixin):
         m.lm_ln_w, m.lm_ln_b = f32(self.lm_head.layer_norm.weight), f32(self.lm_head.layer_norm.bias)
         m.lm_bias = f32(self.lm_head.bias)
         m.layers = C.cast(layer_array, C.POINTER(L.LayerWeights))
+        if code != L.F32:                                              # LM-head dense GEMM on the tensor cores
+            w16 = self.lm_head.dense.weight.detach().to(L.torch_dtype(code)).contiguous()
+            keep.append(w16)
+            m.lm_dense_w16 = w16.data_ptr()
         self._wstruct = (key, m, keep)
         return m
 
@@ -161,17 +186,8 @@ class MSATransformer(nn.Module, _PrecisionMixin):
         L.device_check(tokens.device)
         B, R, Cc = tokens.shape
         D, H, N = self.embed_dim, self.num_attention_heads, self.num_layers
-        if self.msa_position_embedding is not None and R > 1024:           # model.py:354-359
-            raise RuntimeError(
-                "Using model with MSA position embedding trained on maximum MSA "
-                f"depth of 1024, but received {R} alignments.")
         tokens = tokens.long().contiguous()
-        padding_mask = tokens.eq(self.vocab.pad_idx)
-        has_pad = bool(padding_mask.any())                                 # host sync, as model.py:347
-        n_nonpad_max = int((~padding_mask).sum(-1).max()) if has_pad else Cc
-        if n_nonpad_max + self.vocab.pad_idx >= self.embed_positions.weight.shape[0]:
-            raise IndexError(                                              # F.embedding would raise, modules.py:292
-                f"sequence length {Cc} exceeds the {self.embed_positions.max_positions} learned positions")
+        has_pad, _ = self.check_tokens(tokens)                             # model.py:347, 354-359; modules.py:292
         repr_layers = set(repr_layers)
         code = self._code
         dev = tokens.device
@@ -234,20 +250,12 @@ class MSATransformer(nn.Module, _PrecisionMixin):
         L.device_check(dev)
         n = len(grids)
         Rs, Cs = [g.shape[0] for g in grids], [g.shape[1] for g in grids]
-        for R, Cc in zip(Rs, Cs):
-            if self.msa_position_embedding is not None and R > 1024:       # model.py:354-359
-                raise RuntimeError(
-                    "Using model with MSA position embedding trained on maximum MSA "
-                    f"depth of 1024, but received {R} alignments.")
         flat = torch.cat([g.reshape(-1) for g in grids])
         is_pad = flat.eq(self.vocab.pad_idx)
         sizes = [R * Cc for R, Cc in zip(Rs, Cs)]
         pad_counts = torch.stack([c.sum() for c in is_pad.split(sizes)]).tolist()      # one host sync for the batch
-        for g, cnt, Cc in zip(grids, pad_counts, Cs):
-            n_nonpad_max = int((~g.eq(self.vocab.pad_idx)).sum(-1).max()) if cnt else Cc
-            if n_nonpad_max + self.vocab.pad_idx >= self.embed_positions.weight.shape[0]:
-                raise IndexError(
-                    f"sequence length {Cc} exceeds the {self.embed_positions.max_positions} learned positions")
+        for g, cnt, R, Cc in zip(grids, pad_counts, Rs, Cs):
+            self.check_msa_shape(R, Cc, int((~g.eq(self.vocab.pad_idx)).sum(-1).max()) if cnt else Cc)
         has_pad = bytes(1 if c else 0 for c in pad_counts)
         T = sum(sizes)
         x = torch.empty((T, D), dtype=torch.float32, device=dev)

@@ -350,7 +350,8 @@ class AxialTransformerLayer(nn.Module, _PrecisionMixin):
                 pad = _pad_u8(self_attn_padding_mask, b)
                 pm = torch.empty((H, Cc, Cc), dtype=torch.float32, device=x.device) if need_head_weights else None
                 L.check(L.lib.rnamsm_layer_forward(C.byref(w), D, H, F, eps, L.ptr(xb), R, Cc, L.ptr(pad), code,
-                                                   L.ptr(pm), L.ptr(ws), nbytes, L.stream_ptr()), "layer_forward")
+                                                   L.ptr(pm), L.ptr(ws), nbytes, 0, None, None, 0, L.stream_ptr()),
+                        "layer_forward")
                 y[:, :, b, :] = xb
                 if need_head_weights:
                     row_attn[:, b] = pm

@@ -166,9 +166,7 @@ class CudaShardOps:
     def embed(self, tokens_rows: torch.Tensor, r0: int, R_global: int) -> torch.Tensor:
         L, m = self.L, self.m
         Rn, C = tokens_rows.shape
-        if m.msa_position_embedding is not None and R_global > 1024:
-            raise RuntimeError("Using model with MSA position embedding trained on maximum MSA depth of 1024, "
-                               f"but received {R_global} alignments.")
+        m.check_msa_shape(R_global, C, int(tokens_rows.ne(m.vocab.pad_idx).sum(-1).max()))   # this rank's rows
         x = torch.empty((Rn * C, self.D), dtype=torch.float32, device=self.dev)
         row_pos = None
         if m.msa_position_embedding is not None:
@@ -512,9 +510,6 @@ class FusedShardedForward:
         N, D, H = m.num_layers, m.embed_dim, m.num_attention_heads
         if Cn % 16:
             raise ValueError(f"fused schedule needs C / ranks = {Cn} to be a multiple of 16 (TMA box rows)")
-        if m.msa_position_embedding is not None and R > 1024:
-            raise RuntimeError("Using model with MSA position embedding trained on maximum MSA depth of 1024, "
-                               f"but received {R} alignments.")
         code, row_code = self.code, self.row_code
         dt, row_dt = L.torch_dtype(code), L.torch_dtype(row_code)
         if self._flags is None:

@@ -41,7 +41,7 @@ def test_ctypes_struct_layout_matches_header():
     assert C.sizeof(_lib.AttnWeights) == 7 * p                # 6 pointers + int dtype (padded)
     assert _lib.AttnWeights.dtype.offset == 6 * p
     assert C.sizeof(_lib.LayerWeights) == 2 * 7 * p + 6 * p
-    assert C.sizeof(_lib.ModelWeights) == 8 * 4 + 13 * p      # 7 ints + float, then 13 pointers
+    assert C.sizeof(_lib.ModelWeights) == 8 * 4 + 14 * p      # 7 ints + float, then 14 pointers
     assert _lib.ModelWeights.tok_emb.offset == 32
 
 

@@ -136,6 +136,45 @@ def test_linear_residual(L, M, N, K, code):
     assert rel(out, ref) < (2e-5 if code == 0 else 1e-5)   # fp32 output in both modes
 
 
+@pytest.mark.parametrize("M,K,tr", [(129, 768, None), (256, 768, None), (1000, 3072, (40, 25)), (3000, 768, (30, 100)),
+                                    (40000, 768, None)])
+@pytest.mark.parametrize("code,ycode", [(2, 2), (1, 1), (2, 1)], ids=["f16", "bf16", "f16_to_bf16"])
+def test_linear_residual_layernorm(L, M, K, tr, code, ycode):
+    """The fused NormalizedResidualBlock epilogue: the residual stream must equal the plain residual GEMM's bit for bit,
+    and the LayerNorm rows must equal the stand-alone LayerNorm kernel's on that stream bit for bit (same arithmetic),
+    including the transposed output order, tails (M % 256 != 0) and more m-blocks than CTA pairs (40000 rows)."""
+    N = D
+    x, W, bias = gen((M, K), 8), gen((N, K), 9, 0.05), gen((N,), 10, 0.1)
+    resid = gen((M, N), 11)
+    lw, lb = (1 + 0.1 * gen((N,), 12)).cuda(), (0.1 * gen((N,), 13)).cuda()
+    dt = L.torch_dtype(code)
+    xd, Wd, bd = x.to(dt).cuda(), W.to(dt).cuda(), bias.cuda()
+    plain = resid.clone().cuda()
+    L.check(L.lib.rnamsm_linear(L.ptr(xd), L.ptr(Wd), L.ptr(bd), M, N, K, code, 2, 1.0, 0, None, L.ptr(plain), L.stream_ptr()))
+    y_plain = torch.empty(M, N, dtype=L.torch_dtype(ycode), device="cuda")
+    trR, trC = tr if tr else (0, 0)
+    L.check(L.lib.rnamsm_layernorm(L.ptr(plain), L.ptr(lw), L.ptr(lb), L.ptr(y_plain), ycode, M, N, O.LN_EPS, trR, trC,
+                                   L.stream_ptr()))
+    fused = resid.clone().cuda()
+    y = torch.full((M, N), float("nan"), dtype=L.torch_dtype(ycode), device="cuda")
+    counters = torch.zeros(2 * ((M + 255) // 256), dtype=torch.int32, device="cuda")
+    for _ in range(2):                         # twice on the same counters: the kernel must leave them zero
+        fused.copy_(resid)
+        L.check(L.lib.rnamsm_linear_residual_layernorm(L.ptr(xd), L.ptr(Wd), L.ptr(bd), M, N, K, code, L.ptr(fused), L.ptr(lw),
+                                                       L.ptr(lb), O.LN_EPS, L.ptr(y), ycode, trR, trC, L.ptr(counters),
+                                                       L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(counters.abs().sum()) == 0
+    ref = resid.double() + xd.double().cpu() @ Wd.double().cpu().T + bias.double()
+    assert rel(fused, ref) < 1e-5
+    assert torch.equal(fused, plain)
+    assert torch.equal(y, y_plain)
+    ln_ref = O.layer_norm(ref, lw.double().cpu(), lb.double().cpu())
+    if tr:
+        ln_ref = ln_ref.view(trR, trC, N).transpose(0, 1).reshape(M, N)
+    assert rel(y, ln_ref) < (5e-3 if ycode == 1 else 6e-4)
+
+
 # ------------------------------------------------------------------------------------------ K4/K5/K6
 def make_qkv(R, C, seed, code, L, scale=1.0):
     dt = L.torch_dtype(code)

@@ -38,6 +38,17 @@ def test_oracle_cleaning_and_encoding():
     assert np.array_equal(I.encode(seqs), v.encode(seqs))
 
 
+def test_split_records_follows_seqio_record_rules(tmp_path):
+    """Records start at a '>' in column 0 only; blanks inside sequence lines do not count (Bio.SeqIO's FASTA parser,
+    which MSA.from_fasta iterates, utils/align.py:303)."""
+    from rnamsm_b200.ingest import cleaned_length, split_records
+    p = tmp_path / "x.a2m_msa2"
+    p.write_bytes(b"# comment before the first record\n>q a->b |x>y\nAC GU\nacg.U \t\n>second\nACGUU\r\n")
+    headers, raw, off = split_records(str(p))
+    assert headers == ["q a->b |x>y", "second"]
+    assert [cleaned_length(raw[off[i]:off[i + 1]]) for i in range(2)] == [5, 5]
+
+
 def _write_fasta(path, chars, rng):
     """Rows of a cleaned matrix back into a messy a2m file: lowercase insertions, '.', T for U, IUPAC for X."""
     amb = "RYKMSWBDHV"
@@ -52,9 +63,13 @@ def _write_fasta(path, chars, rng):
                 elif ch == "X":
                     ch = str(rng.choice(list(amb)))
                 s += ch
-            f.write(f">seq{n} some description\n")
-            for i in range(0, len(s), 23):                      # wrapped lines
-                f.write(s[i:i + 23] + "\n")
+            f.write(f">seq{n} some description a->b\n")       # a '>' inside a header is text (Bio.SeqIO)
+            for i in range(0, len(s), 23):                      # wrapped lines, some with blanks (SeqIO drops them)
+                line = s[i:i + 23]
+                if rng.random() < 0.3:
+                    k = int(rng.integers(0, len(line) + 1))
+                    line = line[:k] + " " + line[k:] + "  "
+                f.write(line + "\n")
 
 
 @pytest.mark.gpu
