@@ -240,6 +240,16 @@ typedef struct rnamsm_model_weights {
 /* Bytes of scratch rnamsm_layer_forward / rnamsm_msa_forward need for an R x C MSA. */
 size_t rnamsm_workspace_bytes(int R, int C, int D, int H, int F, int dtype);
 
+/* Range diagnostics for the 16-bit path.  rnamsm_range_scan: counters[0] += number of elements of buf (16-bit, n
+ * elements) that are non-finite or sit at the largest finite value of the type (where the kernels' cvt.rn.satfinite
+ * clamps: 65504 for fp16), counters[1] = max(counters[1], float bits of the largest |v| below that).  counters: two
+ * uint64 on the device, zeroed by the caller.  rnamsm_debug_range_watch(counters): while non-NULL, rnamsm_layer_forward /
+ * rnamsm_msa_forward scan every 16-bit activation they write (LayerNorm outputs, q|k|v, attention contexts, post-GELU
+ * hidden) into those counters -- a debugging aid for checkpoints whose activations might leave the fp16 range (then
+ * use precision "bf16"); NULL switches it off (default; process-wide, not thread-safe). */
+int rnamsm_range_scan(const void* buf, long long n, int dtype, unsigned long long* counters, void* stream);
+int rnamsm_debug_range_watch(unsigned long long* counters);
+
 /* One AxialTransformerLayer (modules.py:242-267) in place on x [R*C, D] fp32.
  * pad [R*C] uint8 or NULL.  row_probs_out [H,C,C] fp32 or NULL (then a scratch map is used).
  * With LayerNorm fusion enabled (RNAMSM_FUSE_LN=1, 16-bit path; off by default -- it is exact but measured slower than

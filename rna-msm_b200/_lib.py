@@ -68,6 +68,8 @@ SIGNATURES = {
     "rnamsm_contact_head": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rnamsm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "rnamsm_fused_layernorm": (_i, [_i]),
+    "rnamsm_range_scan": (_i, [_vp, _ll, _i, _vp, _vp]),
+    "rnamsm_debug_range_watch": (_i, [_vp]),
     "rnamsm_layer_forward": (_i, [C.POINTER(LayerWeights), _i, _i, _i, _f, _vp, _i, _i, _vp, _i, _vp, _vp, _sz,
                                   _i, _vp, _vp, _i, _vp]),
     "rnamsm_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
@@ -175,3 +177,21 @@ def profile_collect():
     cnt = (_ll * n)()
     check(lib.rnamsm_profile_collect(ms, cnt, n), "profile_collect")
     return {lib.rnamsm_profile_class_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
+
+
+class RangeWatch:
+    """``with RangeWatch() as w: model(tokens)`` then ``w.saturated`` / ``w.max_abs``: did any 16-bit activation of the
+    forward reach the edge of its type's range (fp16: 65504, where the kernels clamp with satfinite)?  Debugging aid."""
+
+    def __enter__(self):
+        self.counters = torch.zeros(2, dtype=torch.int64, device="cuda")
+        check(lib.rnamsm_debug_range_watch(self.counters.data_ptr()), "debug_range_watch")
+        return self
+
+    def __exit__(self, *exc):
+        check(lib.rnamsm_debug_range_watch(None), "debug_range_watch")
+        torch.cuda.synchronize()
+        c = self.counters.cpu()
+        self.saturated = int(c[0])
+        self.max_abs = float(torch.tensor([int(c[1])], dtype=torch.int64).to(torch.int32).view(torch.float32)[0])
+        return False

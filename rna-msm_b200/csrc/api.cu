@@ -56,6 +56,20 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof_events[reinterpret_cast<size_t>(slot) - 1].b, st);
 }
 
+// RNAMSM_PDL=1 launches the forward's kernels with programmatic dependent launch (each kernel's prologue overlaps its
+// predecessor's tail; all parity tests pass with it).  OFF by default: measured no gain on a B200 -- 512 x 36 (132
+// launches of ~40 us): 5.358 ms plain vs 5.352 ms; 512 x 256: within the box-to-box clock noise -- back-to-back launches
+// on one stream already pipeline, and a persistent 230 KiB CTA cannot become resident before its predecessor's CTA on
+// that SM has exited.
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RNAMSM_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int encode_tmap(CUtensorMap* map, int elem, const void* base, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -181,6 +195,14 @@ static bool fuse_ln_enabled() {
   return v == 1;
 }
 
+// Debug range watch (rnamsm_debug_range_watch): when set, every 16-bit activation the layer writes (LayerNorm outputs,
+// q|k|v, attention contexts, the post-GELU hidden) is scanned for values at the edge of its type's range.
+static unsigned long long* g_range_counters = nullptr;
+static int range_watch(const void* p, long long n, int dtype, cudaStream_t st) {
+  if (g_range_counters == nullptr || !is16(dtype)) return 0;
+  return launch_range_scan(p, n, dtype, g_range_counters, st);
+}
+
 // LayerNorm of the NEXT layer's row block, produced by this layer's fc2 epilogue (16-bit path)
 struct NextLn { const float* w; const float* b; int dtype; };
 
@@ -219,6 +241,7 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS, w->row.b_qkv, q_scale, D, pad};
     if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, row_dt, e, qkv, st))) return rc;
+    if ((rc = range_watch(xn, T * D, row_dt, st)) || (rc = range_watch(qkv, T * 3 * D, row_dt, st))) return rc;
   }
   if (is16(row_dt)) {
     if ((rc = launch_row_logits_16(qkv, R, C, H, row_dt == RNAMSM_F16, partial, p.splits, st))) return rc;
@@ -240,6 +263,7 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->row.b_out, 1.f, 0, nullptr};
     const LnFuse ln{w->col.ln_w, w->col.ln_b, eps, xn, col_dt == RNAMSM_F16, col_major ? R : 0, col_major ? C : 0, cnt};
+    if ((rc = range_watch(ctx, T * D, row_dt, st))) return rc;
     if ((rc = linear_any(ctx, w->row.w_out, T, D, D, row_dt, e, x, st, fuse ? &ln : nullptr))) return rc;
   }
   if (!fuse &&
@@ -262,6 +286,8 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->col.b_out, 1.f, 0, nullptr};
     const LnFuse ln{w->ffn_ln_w, w->ffn_ln_b, eps, xn, dtype == RNAMSM_F16, 0, 0, cnt};
+    if ((rc = range_watch(xn, T * D, col_dt, st)) || (rc = range_watch(ctx, T * D, col_dt, st))) return rc;
+    if (R > 1 && (rc = range_watch(qkv, T * 3 * D, col_dt, st))) return rc;
     if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st, fuse ? &ln : nullptr))) return rc;
   }
 
@@ -270,6 +296,7 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_GELU, w->fc1_b, 1.f, 0, nullptr};
     if ((rc = linear_any(xn, w->fc1_w, T, F, D, dtype, e, qkv, st))) return rc;
+    if ((rc = range_watch(xn, T * D, dtype, st)) || (rc = range_watch(qkv, T * (long long)F, dtype, st))) return rc;
   }
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->fc2_b, 1.f, 0, nullptr};
@@ -536,6 +563,15 @@ int rnamsm_vocab_proj(const float* h, const float* E, const float* bias, long lo
 size_t rnamsm_workspace_bytes(int R, int C, int D, int H, int F, int dtype) {
   if (R <= 0 || C <= 0) return 0;
   return make_plan(R, C, D, H, F, dtype).total;
+}
+
+int rnamsm_range_scan(const void* buf, long long n, int dtype, unsigned long long* counters, void* stream) {
+  RNAMSM_REQUIRE(counters != nullptr, "range_scan: counters required");
+  return launch_range_scan(buf, n, dtype, counters, (cudaStream_t)stream);
+}
+int rnamsm_debug_range_watch(unsigned long long* counters) {
+  g_range_counters = counters;
+  return 0;
 }
 
 int rnamsm_fused_layernorm(int dtype) { return (is16(dtype) && fuse_ln_enabled()) ? 1 : 0; }

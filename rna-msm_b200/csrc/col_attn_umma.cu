@@ -78,6 +78,8 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + BKV;
+  pdl_launch_dependents();
+  pdl_wait();                // programmatic dependent launch: the prologue overlapped the predecessor's tail
 
   const uint32_t idesc_s = make_idesc_16(BQ, BKV, fp16, 0, 0);  // Q (K-major) x K (K-major)
   const uint32_t idesc_o = make_idesc_16(BQ, HD, fp16, 0, 1);   // P (K-major) x V (MN-major)
@@ -265,8 +267,8 @@ int launch_col_attn_small_16(const void* qkv, int R, int C, int H, int fp16, int
   dim3 grid(C, H, ceil_div(R, BQ));
   RNAMSM_REQUIRE(grid.z <= 65535, "col_attn_bf16: R too large");
   ProfScope prof(KC_COL_ATTN, st);
-  col_attn_umma_kernel<<<grid, 128, kSmem, st>>>(tq, tkv, R, C, H, fp16, col_major, pad,
-                                                 reinterpret_cast<uint16_t*>(ctx));
+  RNAMSM_CHECK_CUDA(launch_pdl(col_attn_umma_kernel, grid, dim3(128), kSmem, st, tq, tkv, R, C, H, fp16, col_major, pad,
+                               reinterpret_cast<uint16_t*>(ctx)));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

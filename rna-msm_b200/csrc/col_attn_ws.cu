@@ -162,6 +162,8 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();                // the prologue above overlapped the predecessor's tail (programmatic dependent launch)
 
   // Single-thread roles: TMA producer = warp 0 lane 0; MMA issuer of tile t = lane 0 of warp 1 + t for
   // t < 3 and lane 1 of warp 0 for t = 3 (two roles on divergent lanes of warp 0: independent thread
@@ -445,7 +447,8 @@ int launch_nt(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& 
   if (sms <= 0) sms = 148;
   const int grid = (int)std::min<long long>(n_items, sms);
   ProfScope prof(KC_COL_ATTN, st);
-  col_attn_ws_kernel<NT, kFp16, kRing><<<grid, K::kThreads, K::kSmem, st>>>(tq, tkv, to, R, C, H, col_major, (int)n_items, pad);
+  RNAMSM_CHECK_CUDA(launch_pdl(col_attn_ws_kernel<NT, kFp16, kRing>, dim3(grid), dim3(K::kThreads), K::kSmem, st, tq, tkv, to, R, C,
+                               H, col_major, (int)n_items, pad));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

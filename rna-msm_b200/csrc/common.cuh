@@ -73,6 +73,14 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// ---- programmatic dependent launch -------------------------------------------------------------
+// With RNAMSM_PDL=1 (off by default: measured no gain, see api.cu) the kernels of the forward are launched with the
+// programmatic-stream-serialization attribute (launch_pdl below): a kernel may START (barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream drains,
+// and blocks in pdl_wait() until the predecessor has completed and its writes are visible.  Rule: no global-memory
+// access before pdl_wait(); pdl_launch_dependents() once this CTA holds every resource it needs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -494,6 +502,25 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
 }
 
 #endif  // __CUDACC__
+
+// Host: launch, with the programmatic-dependent-launch attribute when RNAMSM_PDL=1.
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // Host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed).
 enum { TMAP_BF16 = 0, TMAP_F16 = 1, TMAP_F32 = 2 };

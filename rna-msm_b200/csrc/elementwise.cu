@@ -25,6 +25,8 @@ embed_ln_kernel(const int64_t* __restrict__ tokens, int R, int C, const float* _
                 float* __restrict__ x_out, uint8_t* __restrict__ pad_out) {
   __shared__ int s_pos[kColsPerBlock];
   __shared__ int s_tok[kColsPerBlock];
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.y;
   const int c0 = blockIdx.x * kColsPerBlock;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,6 +91,8 @@ layernorm_kernel(const void* x, const float* __restrict__ w, const float* __rest
                  void* y, long long n_rows, int D, float eps, int tr_R, int tr_C) {  // x may alias y (in-place final LN)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / 128;
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < n_rows;
        row += (long long)gridDim.x * kLnWarps) {
     float4 v[kMaxVec];
@@ -194,6 +198,8 @@ row_softmax_kernel(const float* __restrict__ partial, int n_splits, int H, int C
                    const uint8_t* __restrict__ key_pad, float logit_scale, float* __restrict__ probs_out,
                    void* __restrict__ probs_lp, int ld_lp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * kSmWarps + warp;  // h * C + i
   if (row >= (long long)H * C) return;
   const size_t split_stride = (size_t)H * C * C;
@@ -257,6 +263,42 @@ vocab_proj_kernel(const float* __restrict__ h, const float* __restrict__ E, cons
 }
 
 // -------------------------------------------------------------------------------------------
+// Debug: how close did a 16-bit tensor come to the edge of its range?  counters[0] += elements that are non-finite or
+// sit AT the largest finite value (where cvt.rn.satfinite clamps), counters[1] = max(counters[1], bits of max |v|) as
+// a float.  Grid-stride, one atomic per warp.
+// -------------------------------------------------------------------------------------------
+template <bool kFp16>
+__global__ void __launch_bounds__(256)
+range_scan_kernel(const uint16_t* __restrict__ p, long long n, unsigned long long* __restrict__ counters) {
+  unsigned long long hits = 0;
+  float mx = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint16_t a = p[i] & 0x7fffu;
+    const bool edge = kFp16 ? a >= 0x7bffu : a >= 0x7f7fu;          // max finite (65504 / 3.39e38), inf, nan
+    hits += edge ? 1u : 0u;
+    const float v = kFp16 ? __half2float(__ushort_as_half(a)) : __uint_as_float((uint32_t)a << 16);
+    if (!edge) mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+  if ((threadIdx.x & 31) == 0) {
+    if (hits) atomicAdd(&counters[0], hits);
+    atomicMax(&counters[1], (unsigned long long)__float_as_uint(mx));
+  }
+}
+
+int launch_range_scan(const void* p, long long n, int dtype, unsigned long long* counters, cudaStream_t st) {
+  RNAMSM_REQUIRE(dtype == 1 || dtype == 2, "range_scan: 16-bit tensors only (dtype %d)", dtype);
+  if (n <= 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148LL * 8);
+  if (dtype == 2) range_scan_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(p), n, counters);
+  else range_scan_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(p), n, counters);
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------
 // Launchers
 // -------------------------------------------------------------------------------------------
 int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, int vocab, const float* pos_emb,
@@ -266,8 +308,8 @@ int launch_embed_ln(const int64_t* tokens, int R, int C, const float* tok_emb, i
   RNAMSM_REQUIRE(R > 0 && C > 0 && R <= 65535, "embed_layernorm: bad shape R=%d C=%d", R, C);
   dim3 grid(ceil_div(C, kColsPerBlock), R);
   ProfScope prof(KC_EMBED_LN, st);
-  embed_ln_kernel<<<grid, kEmbWarps * 32, 0, st>>>(tokens, R, C, tok_emb, vocab, pos_emb, n_pos, row_pos, ln_w,
-                                                  ln_b, D, pad_idx, eps, x_out, pad_out);
+  RNAMSM_CHECK_CUDA(launch_pdl(embed_ln_kernel, grid, dim3(kEmbWarps * 32), 0, st, tokens, R, C, tok_emb, vocab, pos_emb, n_pos,
+                               row_pos, ln_w, ln_b, D, pad_idx, eps, x_out, pad_out));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -283,14 +325,14 @@ int launch_layernorm(const float* x, const float* w, const float* b, void* y, in
   ProfScope prof(KC_LAYERNORM, st);
   if (x_dtype != 0) {   // 16-bit input -> fp32 output (the LM head's LayerNorm behind a 16-bit dense GEMM)
     RNAMSM_REQUIRE(y_dtype == 0 && tr_C <= 0 && (x_dtype == 1 || x_dtype == 2), "layernorm: 16-bit input supports fp32 output only");
-    if (x_dtype == 1) layernorm_kernel<0, 1><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, 0, 0);
-    else layernorm_kernel<0, 2><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, 0, 0);
+    if (x_dtype == 1) RNAMSM_CHECK_CUDA(launch_pdl(layernorm_kernel<0, 1>, dim3(blocks), dim3(kLnWarps * 32), 0, st, x, w, b, y, n_rows, D, eps, 0, 0));
+    else RNAMSM_CHECK_CUDA(launch_pdl(layernorm_kernel<0, 2>, dim3(blocks), dim3(kLnWarps * 32), 0, st, x, w, b, y, n_rows, D, eps, 0, 0));
   } else if (y_dtype == 1)
-    layernorm_kernel<1><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
+    RNAMSM_CHECK_CUDA(launch_pdl(layernorm_kernel<1, 0>, dim3(blocks), dim3(kLnWarps * 32), 0, st, x, w, b, y, n_rows, D, eps, tr_R, tr_C));
   else if (y_dtype == 2)
-    layernorm_kernel<2><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
+    RNAMSM_CHECK_CUDA(launch_pdl(layernorm_kernel<2, 0>, dim3(blocks), dim3(kLnWarps * 32), 0, st, x, w, b, y, n_rows, D, eps, tr_R, tr_C));
   else
-    layernorm_kernel<0><<<blocks, kLnWarps * 32, 0, st>>>(x, w, b, y, n_rows, D, eps, tr_R, tr_C);
+    RNAMSM_CHECK_CUDA(launch_pdl(layernorm_kernel<0, 0>, dim3(blocks), dim3(kLnWarps * 32), 0, st, x, w, b, y, n_rows, D, eps, tr_R, tr_C));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -322,11 +364,11 @@ int launch_row_softmax(const float* partial, int n_splits, int H, int C, const u
   if (probs_lp == nullptr) ld_lp = 0;
   ProfScope prof(KC_ROW_SOFTMAX, st);
   if (dtype == 1)
-    row_softmax_kernel<1><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp);
+    RNAMSM_CHECK_CUDA(launch_pdl(row_softmax_kernel<1>, dim3(blocks), dim3(kSmWarps * 32), 0, st, partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp));
   else if (dtype == 2)
-    row_softmax_kernel<2><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp);
+    RNAMSM_CHECK_CUDA(launch_pdl(row_softmax_kernel<2>, dim3(blocks), dim3(kSmWarps * 32), 0, st, partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp));
   else
-    row_softmax_kernel<0><<<blocks, kSmWarps * 32, 0, st>>>(partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp);
+    RNAMSM_CHECK_CUDA(launch_pdl(row_softmax_kernel<0>, dim3(blocks), dim3(kSmWarps * 32), 0, st, partial, n_splits, H, C, key_pad, logit_scale, probs_out, probs_lp, ld_lp));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

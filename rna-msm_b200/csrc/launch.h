@@ -37,6 +37,9 @@ int launch_row_softmax(const float* partial, int n_splits, int H, int C, const u
 int launch_vocab_proj(const float* h, const float* E, const float* bias, long long M, int V, int D, float* out,
                       cudaStream_t st);
 
+// debug: count 16-bit elements at / beyond the largest finite value, track max |v| (counters: 2 x u64 on the device)
+int launch_range_scan(const void* p, long long n, int dtype, unsigned long long* counters, cudaStream_t st);
+
 // Epilogue description shared by the fp32 (FFMA) and 16-bit (tcgen05) linear kernels.
 struct LinearEpilogue {
   int kind;                 // RNAMSM_EPI_*

@@ -253,6 +253,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   cluster_sync();    // both CTAs' barriers initialised and TMEM allocated before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();   // this CTA holds its shared memory and TMEM: the next kernel may begin its own prologue
+  pdl_wait();                // everything above overlapped the predecessor's tail; its results are needed from here on
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) =====================
@@ -631,8 +633,8 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int pairs = (int)std::min<long long>(total, g_max_pairs);
   ProfScope prof(prof_class, st);
   static const PeerMaps no_peers{};
-  umma_gemm_kernel<kVariant, kBN, kLN><<<2 * pairs, kLN ? kThreadsLn : kThreads, kSmemBytes, st>>>(
-      ta, tb, to, g, peers ? *peers : no_peers);
+  RNAMSM_CHECK_CUDA(launch_pdl(umma_gemm_kernel<kVariant, kBN, kLN>, dim3(2 * pairs), dim3(kLN ? kThreadsLn : kThreads),
+                               kSmemBytes, st, ta, tb, to, g, peers ? *peers : no_peers));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -169,6 +169,137 @@ def test_submodules_match_fused_layer(pkg, golden_dir, precision):
         layer.row_self_attention.layer(x, self_attn_mask=torch.ones(1, device="cuda"))
 
 
+def pair_scores(maps):
+    """Scores of all residue pairs i < j from the head-averaged, symmetrised, APC-corrected maps [K, L, L] (the features
+    the contact head regresses on, modules.py:347-366 / utils/tensor.py:98-113)."""
+    m = torch.as_tensor(np.asarray(maps), dtype=torch.float64)
+    f = O.apc(O.symmetrize(m)).mean(0)
+    L_ = f.shape[-1]
+    iu = torch.triu_indices(L_, L_, offset=1)
+    return iu, f[iu[0], iu[1]]
+
+
+def top_pairs(maps, k=None):
+    """Top-L residue pairs (i < j): SURVEY.md 8d's contact-pair gate."""
+    iu, score = pair_scores(maps)
+    order = torch.argsort(score, descending=True)[:(k or int(iu.max()) + 1)]
+    return {(int(iu[0][o]), int(iu[1][o])) for o in order}
+
+
+def ambiguous_pairs(ref_maps, rel_margin=5e-3):
+    """How many pairs sit within rel_margin x (score range) of the reference's own top-L cut: those may legitimately
+    fall on either side of it under any finite-precision arithmetic (near-uniform maps have many such ties)."""
+    iu, score = pair_scores(ref_maps)
+    L_ = int(iu.max()) + 1
+    srt = torch.sort(score, descending=True).values
+    cut = 0.5 * (srt[L_ - 1] + srt[L_])
+    return int(((score - cut).abs() <= rel_margin * (srt[0] - srt[-1])).sum())
+
+
+@pytest.mark.parametrize("precision,min_common", [("fp32", 1.0), ("fp16", 1.0), ("bf16", 0.97)])
+def test_top_L_contact_pairs_config1(pkg, golden_dir, precision, min_common):
+    """north_star: 'identical argmax contact pairs' in the 16-bit path.  BASELINE config 1 (2DRB_1): the top-L pairs of
+    the exported maps must be THE SAME SET as the reference's for fp32 and for the production fp16 path; the bf16 mode
+    may differ in at most one pair of 35 (the reference itself cast to bf16 loses one of 119).  The same
+    pairs must come out of the device contact head (rnamsm_contact_head) fed with our maps vs the oracle's head fed
+    with the reference's maps."""
+    g = np.load(os.path.join(golden_dir, "2DRB_1.npz"))
+    model, sd = build(pkg, g["wseed"], 10, g["sharpen"], precision)
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    out = model(tokens, repr_layers=[10], need_head_weights=True, return_contacts=True, want_logits=False)
+    _, atp = pkg.extract_features(out, model.vocab, 10)
+    ours, ref = top_pairs(atp), top_pairs(g["atp"])
+    common = len(ours & ref) / len(ref)
+    print(f"[2DRB_1/{precision}] top-L pairs in common: {len(ours & ref)}/{len(ref)}")
+    assert common >= min_common
+    # the learned head on the device: logistic regression over the 120 APC'd maps, top-L of ITS scores
+    w = sd["contact_head.regression.weight"].double().view(-1)
+    b = sd["contact_head.regression.bias"].double()
+    feat = O.apc(O.symmetrize(torch.as_tensor(g["atp"], dtype=torch.float64)))
+    ref_c = torch.sigmoid((feat * w[:, None, None]).sum(0) + b)
+    got_c = out["contacts"][0].double().cpu()
+    assert got_c.shape == ref_c.shape
+
+    def pairs(c):
+        L_ = c.shape[-1]
+        iu = torch.triu_indices(L_, L_, offset=1)
+        o = torch.argsort(c[iu[0], iu[1]], descending=True)[:L_]
+        return {(int(iu[0][k]), int(iu[1][k])) for k in o}
+    assert len(pairs(got_c) & pairs(ref_c)) / ref_c.shape[-1] >= min_common
+
+
+def test_top_L_contact_pairs_sharpened(pkg):
+    """Same gate on the chunk-threshold-crossing 96 x 200 shape of test_mid_size_vs_oracle (sharpen 3), fp16 path against
+    the fp32 oracle: the same top-L pair set except for pairs tied with the cut (random-init maps are close to uniform,
+    so a few of the 19 701 pairs always sit within rounding of the L-th score)."""
+    model, sd = build(pkg, 42, 3, 3.0, "fp16")
+    tokens = O.make_tokens(96, 200, 8)
+    ref = O.forward(sd, tokens, repr_layers=[3], need_head_weights=True, num_layers=3, want_logits=False)
+    out = model(tokens.cuda(), repr_layers=[3], need_head_weights=True, want_logits=False)
+    ours = top_pairs(out["row_attentions"][0, :, :, 1:, 1:].reshape(-1, 199, 199).cpu())
+    want = top_pairs(ref["row_attentions"][0, :, :, 1:, 1:].reshape(-1, 199, 199))
+    amb = ambiguous_pairs(ref["row_attentions"][0, :, :, 1:, 1:].reshape(-1, 199, 199))
+    print(f"[mid/fp16] top-L pairs in common: {len(ours & want)}/{len(want)} ({amb} pairs within 0.5 % of the cut)")
+    # identical up to the pairs the reference itself places within 0.5 % (of the score range) of its own top-L cut
+    assert len(ours & want) >= len(want) - (amb + 1) // 2 and len(want) - len(ours & want) <= 3
+
+
+def test_fp16_range_stress_and_watch(pkg):
+    """fp16 range safety: every fp32 -> fp16 conversion in the kernels is cvt.rn.satfinite, the residual
+    stream / LayerNorm statistics / softmax stay fp32.  Stress: scale the FFN's first layer so the post-GELU hidden
+    reaches (a) 2.3e4 -- inside the range: the range watch must report no saturation and parity must hold -- and
+    (b) 8e4 -- beyond 65504: the watch must report it, every output must stay finite (no inf / nan: the clamp
+    saturates instead of overflowing) and the damage stays local: the maps' row-argmax still agrees with the UNCLAMPED
+    fp32 oracle on >= 98 % of rows (the fp32 oracle with the same clamp applied agrees on 99.5 %)."""
+    from rnamsm_b200 import _lib as L
+    tokens = O.make_tokens(24, 40, 3)
+
+    def run(scale):
+        sd = O.make_weights(5, num_layers=2, sharpen=2.0)
+        for l in range(2):
+            sd[f"layers.{l}.feed_forward_layer.layer.fc1.weight"] *= scale
+            sd[f"layers.{l}.feed_forward_layer.layer.fc2.weight"] /= scale      # keep the residual stream O(1)
+        vocab = pkg.Vocab(pkg.Alphabet())
+        model = pkg.MSATransformer(vocab, num_layers=2, precision="fp16")
+        model.load_state_dict(sd, strict=True)
+        model = model.eval().cuda()
+        ref = O.forward(sd, tokens, repr_layers=[2], need_head_weights=True, num_layers=2, want_logits=False)
+        with L.RangeWatch() as w:
+            out = model(tokens.cuda(), repr_layers=[2], need_head_weights=True, want_logits=False)
+        return out, ref, w
+
+    out, ref, w = run(8000.0)
+    print(f"[range] scale 8000: max |16-bit activation| {w.max_abs:.3g}, saturated {w.saturated}")
+    assert w.saturated == 0 and 1.5e4 < w.max_abs < 65504
+    assert O.rel_err(out["representations"][2].cpu(), ref["representations"][2]) < BF16_TOL
+    assert O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"]) < BF16_TOL
+    out, ref, w = run(28000.0)
+    print(f"[range] scale 28000: max finite |activation| {w.max_abs:.3g}, saturated {w.saturated}")
+    assert w.saturated > 0                                     # the watch sees the clamp ...
+    assert torch.isfinite(out["representations"][2]).all() and torch.isfinite(out["row_attentions"]).all()
+    assert argmax_agreement(out["row_attentions"].cpu(), ref["row_attentions"]) >= 0.98   # ... and it stays local
+
+
+def test_bf16_mode_beats_the_reference_cast_to_bf16(pkg, golden_dir):
+    """Why the 'bf16' mode is gated at 6e-2 and not at the 2e-2 the fp16 path meets: on BASELINE config 1 bf16 WEIGHTS
+    alone (every activation exact) already put 4.4e-2 on the maps, and the reference itself cast to bf16 9.3e-2
+    (tests/golden/precision_sites_2DRB_1.json, produced by tests/tools/precision_sites.py) -- no bf16-operand path can
+    meet 2e-2 on this input.  Our bf16 mode must stay well below the reference's own bf16 error."""
+    import json
+    fx = json.load(open(os.path.join(golden_dir, "precision_sites_2DRB_1.json")))["results"]
+    ref_bf16 = fx["oracle cast to bf16 (model.bfloat16())"]["atp"]
+    weights_only = fx["only weights bf16"]["atp"]
+    assert weights_only > BF16_TOL and ref_bf16 > BF16_TOL          # the premise, from the committed measurement
+    g = np.load(os.path.join(golden_dir, "2DRB_1.npz"))
+    model, _ = build(pkg, g["wseed"], 10, g["sharpen"], "bf16")
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    out = model(tokens, repr_layers=[10], need_head_weights=True, want_logits=False)
+    _, atp = pkg.extract_features(out, model.vocab, 10)
+    e = O.rel_err(atp, g["atp"])
+    print(f"[2DRB_1/bf16] atp {e:.3e} vs reference-cast-to-bf16 {ref_bf16:.3e}, bf16 weights alone {weights_only:.3e}")
+    assert e < 0.5 * ref_bf16 and e < BF16_MAP_TOL
+
+
 def test_deep_msa_without_row_positions(pkg):
     """R > 1024 is rejected with the row-position embedding (model.py:354-359) and accepted without
     (BASELINE config 4 runs with embed_positions_msa=False); checked against the oracle at 2 layers."""
