@@ -397,17 +397,20 @@ def run_secondary(args, pkg, _lib, world, rank, peaks):
             torch.cuda.empty_cache()
         models.clear()
         torch.cuda.empty_cache()
-        try:                                            # BASELINE configs[1] also names the fp32 path
-            m32 = make_model(True, "fp32")
-            R, C = 512, 256
-            tok = synthetic_tokens(R, C, seed=100).cuda()
-            ms = time_events(lambda: m32(tok, repr_layers=[NL], need_head_weights=True, want_logits=False), 2, 1)
-            out["cfg2_fp32"] = {"workload": WORKLOADS["cfg2"][3] + ", fp32 path", "ms_per_step": round(ms, 2),
-                                "tokens_per_s": round(R * C / (ms * 1e-3), 1),
-                                "whole_forward_tflops": round(total_flops(R, C) / (ms * 1e-3) / 1e12, 1)}
-            del m32
-        except Exception as e:                          # never lose the main line to a secondary measurement
-            out["cfg2_fp32"] = {"error": repr(e)[:200]}
+        for key, prec, what in (("cfg2_fp32", "fp32", "fp32 path (FFMA, the <= 1e-4 parity path)"),
+                                ("cfg2_tf32x3", "tf32x3", "fp32 storage, nn.Linear layers as tf32 x 3 on tcgen05")):
+            try:                                        # BASELINE configs[1] also names the fp32 path
+                m32 = make_model(True, prec)
+                R, C = 512, 256
+                tok = synthetic_tokens(R, C, seed=100).cuda()
+                ms = time_events(lambda: m32(tok, repr_layers=[NL], need_head_weights=True, want_logits=False), 2, 1)
+                out[key] = {"workload": WORKLOADS["cfg2"][3] + ", " + what, "ms_per_step": round(ms, 2),
+                            "tokens_per_s": round(R * C / (ms * 1e-3), 1),
+                            "whole_forward_tflops": round(total_flops(R, C) / (ms * 1e-3) / 1e12, 1)}
+                del m32
+                torch.cuda.empty_cache()
+            except Exception as e:                      # never lose the main line to a secondary measurement
+                out[key] = {"error": repr(e)[:200]}
         return out
 
     # ---------------- N > 1: one MSA sharded over the ranks -----------------------------------------
@@ -672,10 +675,12 @@ def run_ours(args):
         shares = {k: round(v[0] / kernel_ms_total, 4) for k, v in prof.items() if v[1]}
         tflops = {k: round(fl[k] * args.steps / (prof[k][0] * 1e-3) / 1e12, 1) for k in fl if prof.get(k, (0, 0))[0] > 0}
         achieved = gemm_flops_per_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        peak = peaks["bf16_sustained"] if args.precision != "fp32" else None
+        peak = peaks["bf16_sustained"] if args.precision not in ("fp32", "tf32x3") else None
         roofline = {
             "kernel": "umma_gemm_kernel<DENSE> (2-CTA tcgen05 dense linear: QKV / out-proj / fc1+GELU / fc2)"
-                      if args.precision != "fp32" else "sgemm_kernel<LinearProb> (fp32 FFMA)",
+                      if args.precision not in ("fp32", "tf32x3") else
+                      ("umma_gemm_kernel<DENSE, tf32> (three kind::tf32 MMAs on hi / lo operand halves)" if args.precision == "tf32x3"
+                       else "sgemm_kernel<LinearProb> (fp32 FFMA)"),
             "bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
             "frac": round(achieved / peak, 4) if peak else None,
             "peak_source": f"{peaks['source']} bf16_tflops_sustained (cuBLAS bf16; kind::f16 runs fp16 and bf16 at the same "
@@ -702,12 +707,14 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if shard else "weak",
-            "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "bf16_pure": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "bf16_pure": "bf16", "fp32": "f32", "tf32x3": "tf32x3"}[args.precision],
+            "data": "synthetic",
             "config": _config(desc, R, C, tokens_per_step, batch_tokens=(args.batch_tokens if farm else None),
                               tokens_per_step_scope="whole job" if (shard or farm) else "per GPU (x n_gpus independent MSAs)",
                               precision=f"{args.precision}: 16-bit operands on tcgen05 (kind::f16), fp32 accumulate / residual "
-                                        "stream / LayerNorm / softmax / exported maps" if args.precision != "fp32"
-                                        else "fp32 FFMA parity path",
+                                        "stream / LayerNorm / softmax / exported maps" if args.precision not in ("fp32", "tf32x3")
+                                        else ("fp32 FFMA parity path" if args.precision == "fp32" else
+                                              "fp32 storage / attention, nn.Linear layers as tf32 x 3 on tcgen05"),
                               parallelism=(f"one MSA sharded over {world} GPUs: rows (tied row attention, fp32 logit exchange) "
                                            f"<-> columns (column attention, 16-bit re-layout), "
                                            + ("fused peer-memory kernels over NVLink" if args.fused else "NCCL over NVLink")) if shard
@@ -739,7 +746,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "bf16_pure", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "bf16_pure", "tf32x3", "fp32"])
     ap.add_argument("--batch-tokens", type=int, default=0,
                     help="cfg3 only: group the MSAs into forward_batch passes of at most this many tokens "
                          "(0 = one forward per MSA, the reference's B=1 loop)")

@@ -44,6 +44,12 @@ extern "C" {
 #define RNAMSM_ABI_VERSION 3
 
 enum { RNAMSM_F32 = 0, RNAMSM_BF16 = 1, RNAMSM_F16 = 2 };
+/* OR-ed into dtype RNAMSM_F32 for rnamsm_workspace_bytes / rnamsm_layer_forward / rnamsm_msa_forward: fp32 storage and
+ * fp32 attention / LayerNorm / softmax as in the fp32 path, but the nn.Linear layers (88 % of the flops) run on the
+ * tensor cores as rnamsm_linear_tf32 (three tf32 MMAs on hi / lo operand halves).  The tensor core accumulates its fp32
+ * sums with truncation, so this mode is ~10x less exact per GEMM than the FFMA path (measured below) -- a fast
+ * high-precision mode, not the <= 1e-4 parity path. */
+#define RNAMSM_F32_TENSOR 0x100
 #define RNAMSM_MAX_PEERS 8 /* GPUs of one NVSwitch box a single MSA can be sharded over */
 
 /* Epilogues of rnamsm_linear. */
@@ -107,6 +113,18 @@ int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, 
  * partial: fp32 [n_splits, H, C, C].  n_splits >= 1 row ranges are summed by K5. */
 int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, float* partial, int n_splits,
                            void* stream);
+/* fp32 nn.Linear on the tensor cores (the fp32 path's route inside rnamsm_layer_forward / rnamsm_msa_forward): both fp32
+ * operands are split on the device into a tf32 "hi" part and an exact fp32 remainder "lo", and every k-step issues three
+ * tcgen05.mma kind::tf32 into one fp32 accumulator (hi*hi + lo*hi + hi*lo): near-fp32 results (the operand split is
+ * exact to 2^-23; what remains is the tensor core's truncating fp32 accumulation, norm-relative error a few 1e-6,
+ * tests/test_gpu_ops.py) at 8x the FFMA kernel's rate (300 vs 37 TFLOP/s measured).  Same epilogues as rnamsm_linear with
+ * dtype RNAMSM_F32 (out fp32 [M, N]; residual: in place).  scratch: rnamsm_linear_tf32_scratch_bytes(M, N, K) device
+ * bytes, 256 B aligned.  N and K multiples of 32. */
+size_t rnamsm_linear_tf32_scratch_bytes(long long M, int N, int K);
+int rnamsm_linear_tf32(const float* x, const float* W, const float* bias, long long M, int N, int K, int epilogue,
+                       float q_scale, int q_cols, const uint8_t* row_mask, float* out, void* scratch, size_t scratch_bytes,
+                       void* stream);
+
 /* NormalizedResidualBlock (modules.py:385-401) in one kernel, 16-bit path: resid[M, N] (fp32, in place) += x[M, K] W[N, K]^T
  * + bias, and y[M, N] (16-bit, y_dtype) = LayerNorm(resid) * ln_w + ln_b over the N features of each finished row --
  * the operand of the next block's first GEMM, so no stand-alone LayerNorm pass reads the stream again.  The CTA whose

@@ -53,6 +53,8 @@ SIGNATURES = {
     "rnamsm_embed_layernorm": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "rnamsm_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _f, _i, _i, _vp]),
     "rnamsm_linear": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "rnamsm_linear_tf32_scratch_bytes": (_sz, [_ll, _i, _i]),
+    "rnamsm_linear_tf32": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "rnamsm_linear_residual_layernorm": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp]),
     "rnamsm_row_attn_logits": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "rnamsm_row_attn_splits": (_i, [_i, _i, _i, _i]),
@@ -147,9 +149,18 @@ def dtype_code(precision: str) -> int:
         return BF16
     if precision in ("fp16", "float16", "f16"):
         return F16
-    if precision in ("fp32", "float32", "f32"):
+    if precision in ("fp32", "float32", "f32", "tf32x3"):
         return F32
-    raise ValueError(f"unknown precision {precision!r} (expected 'bf16', 'bf16_pure', 'fp16' or 'fp32')")
+    raise ValueError(f"unknown precision {precision!r} (expected 'fp16', 'bf16', 'bf16_pure', 'tf32x3' or 'fp32')")
+
+
+F32_TENSOR = 0x100
+
+
+def forward_code(precision: str) -> int:
+    """dtype argument of rnamsm_workspace_bytes / rnamsm_layer_forward / rnamsm_msa_forward: 'tf32x3' is the fp32 path
+    with RNAMSM_F32_TENSOR (nn.Linear layers as three-term tf32 products on the tensor cores)."""
+    return dtype_code(precision) | (F32_TENSOR if precision == "tf32x3" else 0)
 
 
 def row_dtype_code(precision: str) -> int:

@@ -125,11 +125,14 @@ int encode_tmap(CUtensorMap* map, int elem, const void* base, int rank, const ui
 //   probs   [H, C, ldp] compute dtype   softmax probabilities for the AV GEMM (16-bit paths only)
 //   map     [H, C, C]   fp32            scratch attention map when the caller does not want it
 //   cnt     [2 T / 256] int32           per (m-block, CTA rank) arrival counters of the fused residual + LayerNorm GEMM
+//   split   fp32 path only              hi / lo halves of the current GEMM's activation and weight (tf32 x 3 product)
 // ---------------------------------------------------------------------------------------------
+static size_t tf32_scratch_bytes(long long M, int N, int K);
+
 struct Plan {
   size_t el;  // bytes per element of the compute dtype
   int splits, ldp;
-  size_t off_xn, off_qkvh, off_partial, off_probs, off_map, off_cnt, total;
+  size_t off_xn, off_qkvh, off_partial, off_probs, off_map, off_cnt, off_split, total;
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -145,7 +148,7 @@ static int pick_splits(int R, int C, int H, int dtype) {
   return ceil_div(R, rps);
 }
 
-static Plan make_plan(int R, int C, int D, int H, int F, int dtype) {
+static Plan make_plan(int R, int C, int D, int H, int F, int dtype, bool f32_tensor = false) {
   Plan p{};
   const size_t T = (size_t)R * C;
   p.el = is16(dtype) ? 2 : 4;
@@ -158,14 +161,34 @@ static Plan make_plan(int R, int C, int D, int H, int F, int dtype) {
   p.off_probs = o;   o += align256(is16(dtype) ? (size_t)H * C * p.ldp * p.el : 0);
   p.off_map = o;     o += align256((size_t)H * C * C * 4);
   p.off_cnt = o;     o += align256(ln_counter_bytes((long long)T));   // arrival counters of the fused LayerNorm epilogue
+  p.off_split = o;   o += (dtype == RNAMSM_F32 && f32_tensor) ? tf32_scratch_bytes((long long)T, std::max(3 * D, F), std::max(D, F)) : 0;
   p.total = o;
   return p;
 }
 
+// fp32 path with RNAMSM_F32_TENSOR: the nn.Linear layers run on the tensor cores as a three-term tf32 product
+// (umma_gemm.cu, kTf32) on hi / lo halves of both operands staged in the workspace's split region.
+static size_t tf32_scratch_bytes(long long M, int N, int K) {
+  return 2 * align256((size_t)M * K * 4) + 2 * align256((size_t)N * K * 4);
+}
+static int linear_tf32(const float* x, const float* W, long long M, int N, int K, const LinearEpilogue& e, float* out,
+                       uint8_t* scratch, cudaStream_t st) {
+  float* xh = reinterpret_cast<float*>(scratch);
+  float* xl = reinterpret_cast<float*>(scratch + align256((size_t)M * K * 4));
+  float* wh = reinterpret_cast<float*>(scratch + 2 * align256((size_t)M * K * 4));
+  float* wl = reinterpret_cast<float*>(scratch + 2 * align256((size_t)M * K * 4) + align256((size_t)N * K * 4));
+  int rc;
+  if ((rc = launch_split_tf32(x, xh, xl, M * K, st))) return rc;
+  if ((rc = launch_split_tf32(W, wh, wl, (long long)N * K, st))) return rc;
+  return launch_linear_tf32(xh, xl, wh, wl, M, N, K, e, out, st);
+}
+
 static int linear_any(const void* x, const void* W, long long M, int N, int K, int dtype, const LinearEpilogue& e,
-                      void* out, cudaStream_t st, const LnFuse* ln = nullptr) {
+                      void* out, cudaStream_t st, const LnFuse* ln = nullptr, uint8_t* tf32_scratch = nullptr) {
   if (is16(dtype)) return launch_linear_16(x, W, M, N, K, dtype == RNAMSM_F16, e, out, st, ln);
   RNAMSM_REQUIRE(ln == nullptr, "linear: LayerNorm fusion exists in the 16-bit path only");
+  if (dtype == RNAMSM_F32 && tf32_scratch != nullptr && N % 32 == 0 && K % 32 == 0)
+    return linear_tf32((const float*)x, (const float*)W, M, N, K, e, (float*)out, tf32_scratch, st);
   if (dtype == RNAMSM_F32)
     return launch_linear_f32((const float*)x, (const float*)W, M, N, K, e, (float*)out, st);
   set_error("unknown dtype %d", dtype);
@@ -209,7 +232,7 @@ struct NextLn { const float* w; const float* b; int dtype; };
 // xn_ready: the workspace's xn region already holds LayerNorm_row(x) (written by the previous layer's fc2 epilogue).
 static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, float eps, float* x, int R, int C,
                          const uint8_t* pad, int dtype, float* row_probs_out, uint8_t* ws, const Plan& p,
-                         cudaStream_t st, bool xn_ready = false, const NextLn* next = nullptr) {
+                         cudaStream_t st, bool xn_ready = false, const NextLn* next = nullptr, bool f32_tensor = false) {
   const long long T = (long long)R * C;
   void* xn = ws + p.off_xn;
   uint8_t* qkv = ws + p.off_qkvh;
@@ -225,6 +248,7 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   // (umma_gemm.cu, kLN) and the stand-alone LayerNorm passes disappear except the very first one (see fuse_ln_enabled()
   // for why this is not the default).
   const bool fuse = is16(dtype) && fuse_ln_enabled();
+  uint8_t* split = (dtype == RNAMSM_F32 && f32_tensor) ? ws + p.off_split : nullptr;   // operand halves of the tf32 x 3 product
   int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
   // the counters are zero between launches (the kernel resets them); a layer that starts a chain zeroes them once
   if (fuse && !xn_ready) RNAMSM_CHECK_CUDA(cudaMemsetAsync(cnt, 0, ln_counter_bytes(T), st));
@@ -240,7 +264,7 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
   const float logit_scale = is16(row_dt) ? 1.0f / sqrtf((float)R) : 1.0f;
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS, w->row.b_qkv, q_scale, D, pad};
-    if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, row_dt, e, qkv, st))) return rc;
+    if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, row_dt, e, qkv, st, nullptr, split))) return rc;
     if ((rc = range_watch(xn, T * D, row_dt, st)) || (rc = range_watch(qkv, T * 3 * D, row_dt, st))) return rc;
   }
   if (is16(row_dt)) {
@@ -264,7 +288,7 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->row.b_out, 1.f, 0, nullptr};
     const LnFuse ln{w->col.ln_w, w->col.ln_b, eps, xn, col_dt == RNAMSM_F16, col_major ? R : 0, col_major ? C : 0, cnt};
     if ((rc = range_watch(ctx, T * D, row_dt, st))) return rc;
-    if ((rc = linear_any(ctx, w->row.w_out, T, D, D, row_dt, e, x, st, fuse ? &ln : nullptr))) return rc;
+    if ((rc = linear_any(ctx, w->row.w_out, T, D, D, row_dt, e, x, st, fuse ? &ln : nullptr, split))) return rc;
   }
   if (!fuse &&
       (rc = launch_layernorm(x, w->col.ln_w, w->col.ln_b, xn, col_dt, T, D, eps, st, col_major ? R : 0, col_major ? C : 0)))
@@ -273,10 +297,10 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
     // single-row shortcut: out_proj(v_proj(x)), modules.py:882-894.  Project with the v rows only.
     LinearEpilogue ev{RNAMSM_EPI_BIAS, w->col.b_qkv + 2 * D, 1.f, 0, nullptr};
     const void* wv = (const uint8_t*)w->col.w_qkv + (size_t)2 * D * D * p.el;
-    if ((rc = linear_any(xn, wv, T, D, D, col_dt, ev, ctx, st))) return rc;
+    if ((rc = linear_any(xn, wv, T, D, D, col_dt, ev, ctx, st, nullptr, split))) return rc;
   } else {
     LinearEpilogue e{RNAMSM_EPI_BIAS, w->col.b_qkv, 1.0f / sqrtf(64.f), D, nullptr};  // q *= scaling, :905
-    if ((rc = linear_any(xn, w->col.w_qkv, T, 3 * D, D, col_dt, e, qkv, st))) return rc;
+    if ((rc = linear_any(xn, w->col.w_qkv, T, 3 * D, D, col_dt, e, qkv, st, nullptr, split))) return rc;
     if (is16(col_dt)) {
       if ((rc = launch_col_attn_16(qkv, R, C, H, col_dt == RNAMSM_F16, col_major, pad, ctx, st))) return rc;
     } else {
@@ -288,21 +312,21 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
     const LnFuse ln{w->ffn_ln_w, w->ffn_ln_b, eps, xn, dtype == RNAMSM_F16, 0, 0, cnt};
     if ((rc = range_watch(xn, T * D, col_dt, st)) || (rc = range_watch(ctx, T * D, col_dt, st))) return rc;
     if (R > 1 && (rc = range_watch(qkv, T * 3 * D, col_dt, st))) return rc;
-    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st, fuse ? &ln : nullptr))) return rc;
+    if ((rc = linear_any(ctx, w->col.w_out, T, D, D, col_dt, e, x, st, fuse ? &ln : nullptr, split))) return rc;
   }
 
   // ---- feed-forward: x += fc2(gelu(fc1(LN(x))))                        modules.py:423-427
   if (!fuse && (rc = launch_layernorm(x, w->ffn_ln_w, w->ffn_ln_b, xn, dtype, T, D, eps, st))) return rc;
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_GELU, w->fc1_b, 1.f, 0, nullptr};
-    if ((rc = linear_any(xn, w->fc1_w, T, F, D, dtype, e, qkv, st))) return rc;
+    if ((rc = linear_any(xn, w->fc1_w, T, F, D, dtype, e, qkv, st, nullptr, split))) return rc;
     if ((rc = range_watch(xn, T * D, dtype, st)) || (rc = range_watch(qkv, T * (long long)F, dtype, st))) return rc;
   }
   {
     LinearEpilogue e{RNAMSM_EPI_BIAS_RESIDUAL, w->fc2_b, 1.f, 0, nullptr};
     LnFuse ln{nullptr, nullptr, eps, xn, 0, 0, 0, cnt};
     if (next) { ln.w = next->w; ln.b = next->b; ln.out_fp16 = next->dtype == RNAMSM_F16; }
-    if ((rc = linear_any(qkv, w->fc2_w, T, D, F, dtype, e, x, st, next ? &ln : nullptr))) return rc;
+    if ((rc = linear_any(qkv, w->fc2_w, T, D, F, dtype, e, x, st, next ? &ln : nullptr, split))) return rc;
   }
   return 0;
 }
@@ -517,6 +541,19 @@ int rnamsm_linear(const void* x, const void* W, const float* bias, long long M, 
   return linear_any(x, W, M, N, K, dtype, e, out, (cudaStream_t)stream);
 }
 
+size_t rnamsm_linear_tf32_scratch_bytes(long long M, int N, int K) { return tf32_scratch_bytes(M, N, K); }
+
+int rnamsm_linear_tf32(const float* x, const float* W, const float* bias, long long M, int N, int K, int epilogue,
+                       float q_scale, int q_cols, const uint8_t* row_mask, float* out, void* scratch, size_t scratch_bytes,
+                       void* stream) {
+  RNAMSM_REQUIRE(epilogue >= 0 && epilogue <= 2, "linear_tf32: unknown epilogue %d", epilogue);
+  RNAMSM_REQUIRE(scratch != nullptr && scratch_bytes >= tf32_scratch_bytes(M, N, K) &&
+                     (reinterpret_cast<uintptr_t>(scratch) & 255) == 0,
+                 "linear_tf32: scratch of %zu bytes (256 B aligned) required", tf32_scratch_bytes(M, N, K));
+  LinearEpilogue e{epilogue, bias, q_scale, q_cols, row_mask};
+  return linear_tf32(x, W, M, N, K, e, out, (uint8_t*)scratch, (cudaStream_t)stream);
+}
+
 int rnamsm_linear_residual_layernorm(const void* x, const void* W, const float* bias, long long M, int N, int K, int dtype,
                                      float* resid, const float* ln_w, const float* ln_b, float eps, void* y, int y_dtype,
                                      int tr_R, int tr_C, int* counters, void* stream) {
@@ -562,7 +599,7 @@ int rnamsm_vocab_proj(const float* h, const float* E, const float* bias, long lo
 
 size_t rnamsm_workspace_bytes(int R, int C, int D, int H, int F, int dtype) {
   if (R <= 0 || C <= 0) return 0;
-  return make_plan(R, C, D, H, F, dtype).total;
+  return make_plan(R, C, D, H, F, dtype & 0xff, (dtype & RNAMSM_F32_TENSOR) != 0).total;
 }
 
 int rnamsm_range_scan(const void* buf, long long n, int dtype, unsigned long long* counters, void* stream) {
@@ -580,14 +617,16 @@ int rnamsm_layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
                          const uint8_t* pad, int dtype, float* row_probs_out, void* workspace, size_t workspace_bytes,
                          int xn_ready, const float* next_ln_w, const float* next_ln_b, int next_ln_dtype, void* stream) {
   RNAMSM_REQUIRE(D == H * 64, "layer_forward: head_dim must be 64 (D=%d H=%d)", D, H);
-  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || is16(dtype), "layer_forward: unknown dtype %d", dtype);
-  const Plan p = make_plan(R, C, D, H, F, dtype);
+  const bool f32_tensor = (dtype & RNAMSM_F32_TENSOR) != 0;
+  dtype &= 0xff;
+  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || (is16(dtype) && !f32_tensor), "layer_forward: unknown dtype %d", dtype);
+  const Plan p = make_plan(R, C, D, H, F, dtype, f32_tensor);
   RNAMSM_REQUIRE(workspace_bytes >= p.total, "layer_forward: workspace %zu < required %zu", workspace_bytes, p.total);
   RNAMSM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "layer_forward: workspace must be 256 B aligned");
   RNAMSM_REQUIRE((next_ln_w == nullptr) == (next_ln_b == nullptr), "layer_forward: next_ln_w and next_ln_b go together");
   const NextLn next{next_ln_w, next_ln_b, block_dtype(next_ln_dtype, dtype)};
   return layer_forward(w, D, H, F, ln_eps, x, R, C, pad, dtype, row_probs_out, (uint8_t*)workspace, p,
-                       (cudaStream_t)stream, xn_ready != 0, next_ln_w ? &next : nullptr);
+                       (cudaStream_t)stream, xn_ready != 0, next_ln_w ? &next : nullptr, f32_tensor);
 }
 
 int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int R, int C, int has_pad, int dtype,
@@ -596,9 +635,11 @@ int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int
   cudaStream_t st = (cudaStream_t)stream;
   const int D = m->embed_dim, H = m->num_heads, F = m->ffn_dim, N = m->num_layers;
   RNAMSM_REQUIRE(D == H * 64, "msa_forward: head_dim must be 64 (D=%d H=%d)", D, H);
-  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || is16(dtype), "msa_forward: unknown dtype %d", dtype);
+  const bool f32_tensor = (dtype & RNAMSM_F32_TENSOR) != 0;
+  dtype &= 0xff;
+  RNAMSM_REQUIRE(dtype == RNAMSM_F32 || (is16(dtype) && !f32_tensor), "msa_forward: unknown dtype %d", dtype);
   RNAMSM_REQUIRE(R >= 1 && C >= 1, "msa_forward: empty MSA (R=%d C=%d)", R, C);
-  const Plan p = make_plan(R, C, D, H, F, dtype);
+  const Plan p = make_plan(R, C, D, H, F, dtype, f32_tensor);
   const size_t T = (size_t)R * C;
   const size_t pad_bytes = (T + 255) & ~(size_t)255;
   RNAMSM_REQUIRE(workspace_bytes >= p.total + pad_bytes, "msa_forward: workspace %zu < required %zu", workspace_bytes,
@@ -620,7 +661,7 @@ int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int
     if (fuse && l + 1 < N)
       next = NextLn{m->layers[l + 1].row.ln_w, m->layers[l + 1].row.ln_b, block_dtype(m->layers[l + 1].row.dtype, dtype)};
     if ((rc = layer_forward(&m->layers[l], D, H, F, m->ln_eps, x, R, C, pad_arg, dtype, map, ws, p, st, fuse && l > 0,
-                            next.w ? &next : nullptr)))
+                            next.w ? &next : nullptr, f32_tensor)))
       return rc;
   }
   // 16-bit path with logits wanted: the LM head's dense GEMM runs on the tensor cores, so it needs the final
@@ -644,7 +685,9 @@ int rnamsm_msa_forward(const rnamsm_model_weights* m, const int64_t* tokens, int
                                  0, dtype)))
         return rc;
     } else {
-      if ((rc = launch_linear_f32(x, m->lm_dense_w, (long long)T, D, D, e, (float*)hbuf, st))) return rc;
+      if ((rc = linear_any(x, m->lm_dense_w, (long long)T, D, D, RNAMSM_F32, e, hbuf, st, nullptr,
+                           (dtype == RNAMSM_F32 && f32_tensor) ? ws + p.off_split : nullptr)))
+        return rc;
       if ((rc = launch_layernorm((const float*)hbuf, m->lm_ln_w, m->lm_ln_b, h32, RNAMSM_F32, (long long)T, D, m->ln_eps, st)))
         return rc;
     }

@@ -18,6 +18,16 @@
 // R = 512 -- O now leaves through shared memory and one asynchronous TMA store per warp.
 // Items are numbered with the query block innermost, so CTAs working at the same moment share K/V
 // through L2.
+// Round 2, measured and dropped: (a) an XU token ring between the NT softmax warps of an SM sub-partition (one warp in
+// its exponential section at a time, token handed on 3/4 of the way through): 593 vs 622 TF/s at 512 x 256, 666 vs
+// 731 at 4096 x 128, 638 vs 704 at 1024 x 1024 -- exclusive use of the XU makes it worse, so the warps are not
+// convoying on it; (b) writing the section as three straight runs (32 FFMA2, 64 MUFU pinned with asm volatile, 32 packs
+// + adds): ptxas re-interleaves them into the same MUFU, MUFU, FADD2, F2FP pattern; (c) ex2.approx.ftz.f16x2 runs at 16
+// RESULTS/clk/SM like the f32 form (tools/micro/mufu_bench.cu on a B200: 15.96 vs 15.98), so it halves MUFU
+// instructions but not XU time; (d) programmatic dependent launch for the prologue: no change.  ncu at 4096 x 128
+// (profiles/r02_ncu_col_attn_cfg4.md): XU 70.5 %, tensor 34.6 %, issue 58 %; top stalls wait 24.7 % (fixed-latency
+// dependencies), MIO 17.6 %, long scoreboard 13.5 % -- every softmax warp is latency-bound at ~2900 cycles per 64-key
+// step with 4 of them per sub-partition (TMEM and the 96-register budget allow no more).
 //
 //   warp 0            TMA producer: Q tiles of the item and a K/V ring, 3-D boxes (64 d x 1 column
 //                     x rows) straight out of the packed q|k|v activation
@@ -102,13 +112,7 @@ __device__ __forceinline__ Item decode_item(int item, int nqb, int H) {
   return it;
 }
 
-// kRing: the NT softmax warps that share an SM sub-partition (same TMEM lane quadrant, one per tile) take turns in
-// their exponential sections.  Without it they fall into a convoy: all NT enter the MUFU-bound section together, share
-// the XU fairly (16 ex2/clk/SM), leave it together and then all do their XU-free work (TMEM load, row max, P store,
-// barriers) while the XU idles -- step time = XU time + everything else (measured 1000 + 525 NT cycles, XU 63 % busy).
-// A token passed round the ring tile 0 -> 1 -> ... (one mbarrier per edge, handed on three quarters of the way through
-// the section to hide the hand-over latency) staggers them for good: one warp owns the XU while the others do the rest.
-template <int NT, bool kFp16, bool kRing>
+template <int NT, bool kFp16>
 __global__ void __launch_bounds__(Cfg<NT>::kThreads, 1)
 col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    const __grid_constant__ CUtensorMap tm_o, int R, int C, int H, int col_major, int n_items,
@@ -128,7 +132,6 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* p_full = bars + 20;
   uint64_t* pv_done = bars + 24;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 28);
-  uint64_t* xu_tok = bars + 32;                 // [4 quadrants][4 tiles]: "the warp of tile t on quadrant q may start its ex2 section"
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -151,7 +154,6 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_init(&p_full[b], 4);
       mbar_init(&pv_done[b], 1);
     }
-    for (int b = 0; b < 16; ++b) mbar_init(&xu_tok[b], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -163,7 +165,7 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_launch_dependents();
-  pdl_wait();                // the prologue above overlapped the predecessor's tail (programmatic dependent launch)
+  pdl_wait();                // RNAMSM_PDL=1: the prologue above overlapped the predecessor's tail
 
   // Single-thread roles: TMA producer = warp 0 lane 0; MMA issuer of tile t = lane 0 of warp 1 + t for
   // t < 3 and lane 1 of warp 0 for t = 3 (two roles on divergent lanes of warp 0: independent thread
@@ -319,16 +321,10 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // word w) overwrite the low half of each sv[hlf] as they are produced
         const uint64_t c_l2e = f32x2_pack(kLog2e, kLog2e), c_negm = f32x2_pack(-m_ref, -m_ref);
         uint64_t acc0 = f32x2_pack(0.f, 0.f), acc1 = acc0;
-        if (kRing) {                                  // our turn on the XU?  (tile 0 starts with the token)
-          if (t > 0) mbar_wait_quiet(&xu_tok[quad * 4 + t], (uint32_t)(g & 1));
-          else if (g > 0) mbar_wait_quiet(&xu_tok[quad * 4], (uint32_t)((g - 1) & 1));
-        }
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
-            if (kRing && hlf == 1 && e == 16 && lane == 0)      // hand the XU on: the rest of this section overlaps the hand-over
-              mbar_arrive(&xu_tok[quad * 4 + (t + 1 == NT ? 0 : t + 1)]);
             const uint64_t x0 = f32x2_fma(f32x2_pack(__uint_as_float(sv[hlf][e]), __uint_as_float(sv[hlf][e + 1])), c_l2e, c_negm);
             const uint64_t x1 = f32x2_fma(f32x2_pack(__uint_as_float(sv[hlf][e + 2]), __uint_as_float(sv[hlf][e + 3])), c_l2e, c_negm);
             float a0, a1, a2, a3;
@@ -430,13 +426,13 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, K::kTmemCols);
 }
 
-template <int NT, bool kFp16, bool kRing>
+template <int NT, bool kFp16>
 int launch_nt(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to, int R, int C, int H, int col_major,
               const uint8_t* pad, cudaStream_t st) {
   using K = Cfg<NT>;
   static bool attr_set = false;
   if (!attr_set) {
-    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_ws_kernel<NT, kFp16, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmem));
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_ws_kernel<NT, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmem));
     attr_set = true;
   }
   const long long n_items = (long long)C * H * ((R + NT * BQ - 1) / (NT * BQ));
@@ -447,8 +443,8 @@ int launch_nt(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& 
   if (sms <= 0) sms = 148;
   const int grid = (int)std::min<long long>(n_items, sms);
   ProfScope prof(KC_COL_ATTN, st);
-  RNAMSM_CHECK_CUDA(launch_pdl(col_attn_ws_kernel<NT, kFp16, kRing>, dim3(grid), dim3(K::kThreads), K::kSmem, st, tq, tkv, to, R, C,
-                               H, col_major, (int)n_items, pad));
+  RNAMSM_CHECK_CUDA(launch_pdl(col_attn_ws_kernel<NT, kFp16>, dim3(grid), dim3(K::kThreads), K::kSmem, st, tq, tkv, to, R, C, H,
+                               col_major, (int)n_items, pad));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -483,17 +479,11 @@ int launch_col_attn_ws_16(const void* qkv, int R, int C, int H, int fp16, int co
     forced = e ? atoi(e) : 0;
   }
   const int nt = forced == 2 || forced == 4 ? forced : (R > 2 * BQ ? 4 : 2);
-  static int ring = -1;
-  if (ring < 0) {
-    const char* e = getenv("RNAMSM_COL_RING");
-    ring = e ? atoi(e) : 0;
-  }
-#define RNAMSM_COL_LAUNCH(NT_, FP_)                                                              \
-  (ring ? launch_nt<NT_, FP_, true>(tq, tkv, to, R, C, H, col_major, pad, st)                     \
-        : launch_nt<NT_, FP_, false>(tq, tkv, to, R, C, H, col_major, pad, st))
-  if (nt == 4) return fp16 ? RNAMSM_COL_LAUNCH(4, true) : RNAMSM_COL_LAUNCH(4, false);
-  return fp16 ? RNAMSM_COL_LAUNCH(2, true) : RNAMSM_COL_LAUNCH(2, false);
-#undef RNAMSM_COL_LAUNCH
+  if (nt == 4)
+    return fp16 ? launch_nt<4, true>(tq, tkv, to, R, C, H, col_major, pad, st)
+                : launch_nt<4, false>(tq, tkv, to, R, C, H, col_major, pad, st);
+  return fp16 ? launch_nt<2, true>(tq, tkv, to, R, C, H, col_major, pad, st)
+              : launch_nt<2, false>(tq, tkv, to, R, C, H, col_major, pad, st);
 }
 
 }  // namespace rnamsm

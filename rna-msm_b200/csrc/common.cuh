@@ -319,6 +319,18 @@ __device__ __forceinline__ void umma_16_2sm(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with tf32 operands (fp32 words in shared memory, the low 13 mantissa bits ignored), K = 8 per instruction.
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on the mbarrier at this smem offset in BOTH CTAs of the pair once all prior MMAs completed.
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
   asm volatile(
@@ -372,6 +384,11 @@ __host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int fp16, int
   const uint32_t fmt = fp16 ? 0u : 1u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::tf32: A / B format 2 (tf32), fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes of work) ------------

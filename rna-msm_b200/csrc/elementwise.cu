@@ -263,6 +263,38 @@ vocab_proj_kernel(const float* __restrict__ h, const float* __restrict__ E, cons
 }
 
 // -------------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) for the three-MMA tf32 product: hi = x rounded TO NEAREST at tf32 precision (10 mantissa bits; low 13
+// bits zero, so it is the same number whether the tensor core truncates or rounds its operands), lo = x - hi (exact in
+// fp32, |lo| <= 2^-11 |x|, either sign) rounded to nearest at tf32 precision as well.  Representation error
+// |x - hi - lo| <= 2^-23 |x| with no systematic sign (plain truncation would bias every term the same way: measured 6e-6
+// instead of 6e-7 norm-relative on a 768-long dot product).
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rn_tf32(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x00001000u) & 0xffffe000u);
+}
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    const float4 h = make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+    hi[i] = h;
+    lo[i] = make_float4(rn_tf32(v.x - h.x), rn_tf32(v.y - h.y), rn_tf32(v.z - h.z), rn_tf32(v.w - h.w));
+  }
+}
+
+int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st) {
+  RNAMSM_REQUIRE(n % 4 == 0 && n > 0, "split_tf32: element count %lld must be a positive multiple of 4", n);
+  const long long n4 = n / 4;
+  const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148LL * 16);
+  ProfScope prof(KC_LAYERNORM, st);
+  split_tf32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
+                                           reinterpret_cast<float4*>(lo), n4);
+  count_launch();
+  RNAMSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------
 // Debug: how close did a 16-bit tensor come to the edge of its range?  counters[0] += elements that are non-finite or
 // sit AT the largest finite value (where cvt.rn.satfinite clamps), counters[1] = max(counters[1], bits of max |v|) as
 // a float.  Grid-stride, one atomic per warp.

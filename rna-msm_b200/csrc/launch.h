@@ -78,6 +78,11 @@ inline size_t ln_counter_bytes(long long M) { return (size_t)(2 * ((M + 255) / 2
 // umma_gemm.cu -- 16-bit (bf16 / fp16 operands, fp32 accumulate) tcgen05 path; fp16 != 0 selects fp16
 int launch_linear_16(const void* x, const void* W, long long M, int N, int K, int fp16, const LinearEpilogue& epi,
                      void* out, cudaStream_t st, const LnFuse* ln = nullptr);
+// fp32 linear on the tensor cores: hi / lo tf32 split of both operands, three kind::tf32 MMAs per k-step
+int launch_linear_tf32(const float* x_hi, const float* x_lo, const float* W_hi, const float* W_lo, long long M, int N, int K,
+                       const LinearEpilogue& epi, float* out, cudaStream_t st);
+// hi = x with the low 13 mantissa bits cleared (a tf32 number), lo = x - hi (exact); n elements
+int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
 int launch_row_logits_16(const void* qkv, int R, int C, int H, int fp16, float* partial, int n_splits, cudaStream_t st);
 int launch_row_av_16(const void* probs, int ldp, const void* qkv, int R, int C, int H, int fp16, void* ctx,
                      cudaStream_t st);

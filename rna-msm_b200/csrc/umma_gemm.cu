@@ -21,6 +21,12 @@
 // Operand element type is bf16 or fp16 (same tensor-core rate, kind::f16); fp16 carries three more
 // mantissa bits and is what the tied row-attention block uses (see api.cu).
 //
+//   DENSE, kTf32 : the fp32 path's nn.Linear on the tensor cores.  fp32 operands are split on the device into
+//           hi = the value rounded to nearest at tf32 precision and lo = the (exact) remainder x - hi rounded likewise
+//           (|x - hi - lo| <= 2^-23 |x|), and every k-step issues three tcgen05.mma kind::tf32 into the same fp32
+//           accumulator: lo*hi + hi*lo + hi*hi (the dropped lo*lo term is 2^-22 of the product, of either sign) --
+//           fp32-grade results at a third of the tf32 rate: measured 300 TF/s against the FFMA kernel's 37.
+//
 // Warp roles (384 threads per CTA): warp 0 = TMA producer (one elected lane, both CTAs), warp 1 =
 // MMA issuer (one elected lane, leader CTA only), warp 2 = TMEM allocation, warp 3 idle,
 // warps 4..11 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4).
@@ -43,7 +49,7 @@ constexpr int BLOCK_N = 256;                     // accumulator columns per pair
 constexpr int HALF_N = BLOCK_N / 2;
 constexpr int BLOCK_K = 64;                      // one SWIZZLE_128B atom of 16-bit elements along K
 constexpr int UMMA_K = 16;
-constexpr int kStages = 6;
+constexpr int kStagesDefault = 6;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int B_BYTES = HALF_N * BLOCK_K * 2;    // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KiB per CTA per k-block
@@ -57,7 +63,7 @@ constexpr int kThreadsLn = kThreads + 32 * kLnWarps;
 constexpr int kLnMaxVec = 8;                     // N <= 8 * 128 features per row
 constexpr int kLnSlots = 4;                      // tiles the epilogue may run ahead of the LayerNorm warps
 constexpr int EPI_BUF_BYTES = 32 * 128;          // one 32-row x 128 B staging box per epilogue warp
-constexpr int kSmemBytes = kStages * STAGE_BYTES + kEpiWarps * EPI_BUF_BYTES + 256 + 1024;
+constexpr int kSmemBytes = kStagesDefault * STAGE_BYTES + kEpiWarps * EPI_BUF_BYTES + 256 + 1024;
 
 enum { V_DENSE = 0, V_TIED = 1, V_AV = 2 };
 
@@ -195,13 +201,18 @@ __device__ __forceinline__ void stage_row(uint8_t* buf, int lane, const uint32_t
 
 // kBN = accumulator columns of the pair tile (256; 128 / 64 for the tied logits of short alignments, where a
 // 256-wide tile would be mostly padding): each CTA stages kBN / 2 rows of B, TMEM holds 2 x kBN columns.
-template <int kVariant, int kBN, bool kLN = false>
+template <int kVariant, int kBN, bool kLN = false, bool kTf32 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLN ? kThreadsLn : kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g,
                  const __grid_constant__ PeerMaps peers) {
   constexpr int BN = kBN, HN = kBN / 2;
-  constexpr int STG = A_BYTES + HN * BLOCK_K * 2;        // bytes per CTA per k-block
+  // bytes per CTA per k-block: A + B tiles (16-bit: 64 elements of K per 128 B row); kTf32: hi and lo tiles of both
+  // operands (fp32: 32 elements of K per 128 B row) in a shallower ring
+  constexpr int STG = kTf32 ? 4 * A_BYTES : A_BYTES + HN * BLOCK_K * 2;
+  constexpr int kStages = kTf32 ? 3 : kStagesDefault;
+  constexpr int KB_ELEMS = kTf32 ? 32 : BLOCK_K;         // K elements per k-block
+  static_assert(!kTf32 || (kVariant == V_DENSE && kBN == BLOCK_N && !kLN), "tf32 split: the dense 256-wide variant only");
   constexpr int TMC = 2 * kBN;                           // TMEM columns (power of two >= 32)
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment (descriptor base_offset = 0).  The dynamic smem
@@ -269,7 +280,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sb = sa + A_BYTES;
           const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's full barrier
           mbar_expect_tx_cluster(bar, STG);
-          if (kVariant == V_DENSE) {
+          if (kTf32) {            // [A hi | A lo | B hi | B lo], the lo operands through peers.m[0] / m[1]
+            tma_load_3d_2sm(sa, &tmap_a, bar, kb * KB_ELEMS, t.m0 + cta_rank * BLOCK_M, 0);
+            tma_load_3d_2sm(sa + A_BYTES, &peers.m[0], bar, kb * KB_ELEMS, t.m0 + cta_rank * BLOCK_M, 0);
+            tma_load_3d_2sm(sa + 2 * A_BYTES, &tmap_b, bar, kb * KB_ELEMS, t.n0 + cta_rank * HN, 0);
+            tma_load_3d_2sm(sa + 3 * A_BYTES, &peers.m[1], bar, kb * KB_ELEMS, t.n0 + cta_rank * HN, 0);
+          } else if (kVariant == V_DENSE) {
             tma_load_3d_2sm(sa, &tmap_a, bar, kb * BLOCK_K, t.m0 + cta_rank * BLOCK_M, 0);
             tma_load_3d_2sm(sb, &tmap_b, bar, kb * BLOCK_K, t.n0 + cta_rank * HN, 0);
           } else if (kVariant == V_TIED) {
@@ -287,7 +303,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA) =====================
     if (leader && elect_one()) {
-      const uint32_t idesc = make_idesc_16(PAIR_M, BN, g.fp16, 0, kVariant == V_AV ? 1 : 0);
+      const uint32_t idesc = kTf32 ? make_idesc_tf32(PAIR_M, BN) : make_idesc_16(PAIR_M, BN, g.fp16, 0, kVariant == V_AV ? 1 : 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int lt = 0, tile; (tile = tile_at(lt, pair, n_pairs, total_tiles)) >= 0; ++lt) {
@@ -300,6 +316,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STG);
           const uint32_t b_addr = a_addr + A_BYTES;
+          if (kTf32) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {            // 32 fp32 per row = 4 k-steps of 8 (32 B each)
+              const uint64_t a_hi = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t a_lo = make_smem_desc_sw128(a_addr + A_BYTES + k * 32, 16, 1024);
+              const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * A_BYTES + k * 32, 16, 1024);
+              const uint64_t b_lo = make_smem_desc_sw128(a_addr + 3 * A_BYTES + k * 32, 16, 1024);
+              umma_tf32_2sm(d_tmem, a_lo, b_hi, idesc, (uint32_t)((kb | k) != 0));   // small terms first
+              umma_tf32_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // A: K-major, 128 B rows, 8-row groups 1024 B apart; +32 B per 16-element k step.
@@ -417,6 +445,38 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // L2 (not merely read out of the staging buffer): tell the LayerNorm warps, one tile late and without stalling
           bulk_wait_pending<HN / 32>();
           ln_signal(lt - 1);
+        }
+      } else if (kTf32) {
+        // fp32 outputs (bias, q scale / row mask, exact erf-GELU as in the FFMA path): 32-column boxes, TMA store
+#pragma unroll 1
+        for (int c = 0; c < HN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == HN / 32 - 1) release_acc();
+          const int n = t.n0 + half * HN + c * 32;
+          if (n >= g.N || row0 >= g.M) continue;
+          float s = 1.f;
+          if (g.epi_kind == RNAMSM_EPI_BIAS && n < g.q_cols) {   // q_cols is a multiple of 64
+            const int m = row0 + lane;
+            s = (g.row_mask && m < g.M && g.row_mask[m]) ? 0.f : g.q_scale;
+          }
+          const bool gelu = g.epi_kind == RNAMSM_EPI_BIAS_GELU;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            float a = __uint_as_float(v[k]) + g.bias[n + k];
+            a = gelu ? gelu_erf(a) : a * s;
+            v[k] = __float_as_uint(a);
+          }
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          stage_row(buf, lane, v);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_out, buf, n, row0, 0);
+            bulk_commit();
+          }
         }
       } else {
         // 16-bit outputs: 64-column boxes (128 B rows), TMA store
@@ -618,12 +678,12 @@ static void ensure_max_pairs() {
   g_max_pairs = std::max(1, std::min(n, num_sms() / 2));
 }
 
-template <int kVariant, int kBN = BLOCK_N, bool kLN = false>
+template <int kVariant, int kBN = BLOCK_N, bool kLN = false, bool kTf32 = false>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g,
                    int prof_class, cudaStream_t st, const PeerMaps* peers = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
-    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant, kBN, kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant, kBN, kLN, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes));
     attr_set = true;
   }
@@ -633,7 +693,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int pairs = (int)std::min<long long>(total, g_max_pairs);
   ProfScope prof(prof_class, st);
   static const PeerMaps no_peers{};
-  RNAMSM_CHECK_CUDA(launch_pdl(umma_gemm_kernel<kVariant, kBN, kLN>, dim3(2 * pairs), dim3(kLN ? kThreadsLn : kThreads),
+  RNAMSM_CHECK_CUDA(launch_pdl(umma_gemm_kernel<kVariant, kBN, kLN, kTf32>, dim3(2 * pairs), dim3(kLN ? kThreadsLn : kThreads),
                                kSmemBytes, st, ta, tb, to, g, peers ? *peers : no_peers));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
@@ -701,6 +761,36 @@ int launch_linear_16(const void* x, const void* W, long long M, int N, int K, in
     return launch_variant<V_DENSE, BLOCK_N, true>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
   }
   return launch_variant<V_DENSE>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
+}
+
+// fp32 nn.Linear on the tensor cores: x = x_hi + x_lo, W = W_hi + W_lo (split_tf32 in elementwise.cu), three tf32 MMAs per
+// k-step.  out: fp32 [M, N] (bias / bias+GELU epilogues: plain store; residual epilogue: reduce-add in place).
+int launch_linear_tf32(const float* x_hi, const float* x_lo, const float* W_hi, const float* W_lo, long long M, int N, int K,
+                       const LinearEpilogue& epi, float* out, cudaStream_t st) {
+  RNAMSM_REQUIRE(M > 0 && M < (1LL << 31), "linear_tf32: M=%lld out of range", M);
+  RNAMSM_REQUIRE(N % 32 == 0 && K % 32 == 0 && K >= 32, "linear_tf32: N=%d and K=%d must be multiples of 32", N, K);
+  RNAMSM_REQUIRE(epi.bias != nullptr && epi.q_cols % 64 == 0, "linear_tf32: bias required, q_cols a multiple of 64");
+  CUtensorMap ta, tb, to;
+  PeerMaps lo{};
+  uint64_t adims[3] = {(uint64_t)K, (uint64_t)M, 1}, astr[2] = {(uint64_t)K * 4, (uint64_t)M * K * 4};
+  uint64_t bdims[3] = {(uint64_t)K, (uint64_t)N, 1}, bstr[2] = {(uint64_t)K * 4, (uint64_t)N * K * 4};
+  uint32_t abox[3] = {32, BLOCK_M, 1}, bbox[3] = {32, HALF_N, 1};
+  if (encode_tmap(&ta, TMAP_F32, x_hi, 3, adims, astr, abox)) return 3;
+  if (encode_tmap(&lo.m[0], TMAP_F32, x_lo, 3, adims, astr, abox)) return 3;
+  if (encode_tmap(&tb, TMAP_F32, W_hi, 3, bdims, bstr, bbox)) return 3;
+  if (encode_tmap(&lo.m[1], TMAP_F32, W_lo, 3, bdims, bstr, bbox)) return 3;
+  uint64_t odims[3] = {(uint64_t)N, (uint64_t)M, 1}, ostr[2] = {(uint64_t)N * 4, (uint64_t)M * N * 4};
+  uint32_t obox[3] = {32, 32, 1};
+  if (encode_tmap(&to, TMAP_F32, out, 3, odims, ostr, obox)) return 3;
+  GemmArgs g{};
+  g.m_tiles = ceil_div(M, PAIR_M);
+  g.n_tiles = ceil_div(N, BLOCK_N);
+  g.batches = 1; g.splits = 1;
+  g.k_blocks = K / 32;
+  g.M = (int)M; g.N = N;
+  g.epi_kind = epi.kind; g.bias = epi.bias; g.q_scale = epi.q_scale; g.q_cols = epi.q_cols; g.row_mask = epi.row_mask;
+  g.out = out; g.ld_out = N;
+  return launch_variant<V_DENSE, BLOCK_N, false, true>(ta, tb, to, g, linear_class(epi.kind, N, K), st, &lo);
 }
 
 // Column block's out-projection of the sharded forward: ctx [R*Cn, K] (this rank's column shard, token-major

@@ -64,7 +64,8 @@ def extract_features_streamed(model: MSATransformer, tokens: torch.Tensor, atp_h
         pad = torch.empty(R * Cc, dtype=torch.uint8, device=dev)
         maps = torch.empty((N, H, Cc, Cc), dtype=torch.float32, device=dev)
         m = model.c_weights(code)
-        nbytes = L.lib.rnamsm_workspace_bytes(R, Cc, D, H, 4 * D, code)
+        fcode = model._fwd_code
+        nbytes = L.lib.rnamsm_workspace_bytes(R, Cc, D, H, 4 * D, fcode)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         st = L.stream_ptr()
         L.check(L.lib.rnamsm_embed_layernorm(L.ptr(tok[0]), R, Cc, m.tok_emb, m.vocab, m.pos_emb, m.n_pos, m.row_pos,
@@ -74,7 +75,7 @@ def extract_features_streamed(model: MSATransformer, tokens: torch.Tensor, atp_h
         for l in range(N):
             nxt = m.layers[l + 1].row if (chain and l + 1 < N) else None
             L.check(L.lib.rnamsm_layer_forward(C.byref(m.layers[l]), D, H, 4 * D, m.ln_eps, L.ptr(x), R, Cc,
-                                               L.ptr(pad) if has_pad else None, code, L.ptr(maps[l]), L.ptr(ws), nbytes,
+                                               L.ptr(pad) if has_pad else None, fcode, L.ptr(maps[l]), L.ptr(ws), nbytes,
                                                int(chain and l > 0), nxt.ln_w if nxt is not None else None,
                                                nxt.ln_b if nxt is not None else None, nxt.dtype if nxt is not None else 0, st),
                     "layer_forward")
@@ -273,7 +274,7 @@ def main(argv=None):
     ap.add_argument("--num_attention_heads", type=int, default=12)
     ap.add_argument("--num_layers", type=int, default=10)
     ap.add_argument("--no_embed_positions_msa", action="store_true")
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "bf16_pure", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "bf16_pure", "tf32x3", "fp32"])
     a = ap.parse_args(argv)
     model, vocab = build_model(a.model_path, a.device, a.precision, a.embed_dim, a.num_attention_heads, a.num_layers,
                                not a.no_embed_positions_msa, a.max_tokens, a.max_seqlen)

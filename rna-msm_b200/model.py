@@ -198,13 +198,14 @@ class MSATransformer(nn.Module, _PrecisionMixin):
             l: torch.empty((B, R, Cc, D), dtype=torch.float32, device=dev) for l in sorted(repr_layers) if 0 <= l < N}
         with torch.cuda.device(dev):
             m = self.c_weights(code)
-            nbytes = L.lib.rnamsm_workspace_bytes(R, Cc, D, H, 4 * D, code) + ((R * Cc + 255) // 256) * 256
+            fcode = self._fwd_code
+            nbytes = L.lib.rnamsm_workspace_bytes(R, Cc, D, H, 4 * D, fcode) + ((R * Cc + 255) // 256) * 256
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             st = L.stream_ptr()
             for b in range(B):
                 rep_ptrs = (C.c_void_p * (N + 1))(*[reps[l][b].data_ptr() if l in reps else None for l in range(N + 1)])
                 L.check(L.lib.rnamsm_msa_forward(
-                    C.byref(m), L.ptr(tokens[b]), R, Cc, int(has_pad), code, L.ptr(x[b]),
+                    C.byref(m), L.ptr(tokens[b]), R, Cc, int(has_pad), fcode, L.ptr(x[b]),
                     L.ptr(row_att[b]) if row_att is not None else None, rep_ptrs,
                     L.ptr(logits[b]) if logits is not None else None, L.ptr(ws), nbytes, st), "msa_forward")
         if N in repr_layers:

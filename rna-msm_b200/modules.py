@@ -40,7 +40,9 @@ def _pad_u8(self_attn_padding_mask: Optional[torch.Tensor], b: int) -> Optional[
 class _PrecisionMixin:
     """``precision``: 'fp16' (default: fp16 operands on the tcgen05 tensor cores, fp32 accumulate /
     residual stream / LayerNorm / softmax), 'bf16' (bf16 operands except the tied row-attention
-    block, which stays fp16), 'bf16_pure' (bf16 everywhere) or 'fp32' (FFMA parity path)."""
+    block, which stays fp16), 'bf16_pure' (bf16 everywhere), 'fp32' (FFMA parity path, <= 1e-4) or 'tf32x3' (fp32
+    storage and attention, the nn.Linear layers as three-term tf32 products on the tensor cores: 3x faster than 'fp32',
+    ~1e-4-grade rather than 1e-5-grade because the tensor core truncates when it accumulates)."""
 
     precision: str = _DEFAULT_PRECISION
 
@@ -58,6 +60,11 @@ class _PrecisionMixin:
     @property
     def _row_code(self) -> int:
         return L.row_dtype_code(self.precision)
+
+    @property
+    def _fwd_code(self) -> int:
+        """dtype for the whole-layer / whole-model C entry points (carries the tf32x3 flag)."""
+        return L.forward_code(self.precision)
 
 
 def _linear(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, code: int, epilogue: int = L.EPI_BIAS,
@@ -341,7 +348,8 @@ class AxialTransformerLayer(nn.Module, _PrecisionMixin):
         row_attn = torch.empty((H, B, Cc, Cc), dtype=torch.float32, device=x.device) if need_head_weights else None
         with torch.cuda.device(x.device):
             w = self.c_weights(code)
-            nbytes = L.lib.rnamsm_workspace_bytes(R, Cc, D, H, F, code)
+            fcode = self._fwd_code
+            nbytes = L.lib.rnamsm_workspace_bytes(R, Cc, D, H, F, fcode)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             for b in range(B):
                 # fresh fp32 copy (never a view of the caller's x): the kernels update it in place
@@ -349,7 +357,7 @@ class AxialTransformerLayer(nn.Module, _PrecisionMixin):
                 xb.copy_(x[:, :, b, :])
                 pad = _pad_u8(self_attn_padding_mask, b)
                 pm = torch.empty((H, Cc, Cc), dtype=torch.float32, device=x.device) if need_head_weights else None
-                L.check(L.lib.rnamsm_layer_forward(C.byref(w), D, H, F, eps, L.ptr(xb), R, Cc, L.ptr(pad), code,
+                L.check(L.lib.rnamsm_layer_forward(C.byref(w), D, H, F, eps, L.ptr(xb), R, Cc, L.ptr(pad), fcode,
                                                    L.ptr(pm), L.ptr(ws), nbytes, 0, None, None, 0, L.stream_ptr()),
                         "layer_forward")
                 y[:, :, b, :] = xb

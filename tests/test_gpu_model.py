@@ -300,6 +300,26 @@ def test_bf16_mode_beats_the_reference_cast_to_bf16(pkg, golden_dir):
     assert e < 0.5 * ref_bf16 and e < BF16_MAP_TOL
 
 
+TF32X3_TOL = 1e-3      # 'tf32x3': 20x tighter than the 16-bit gate; measured values are printed
+
+
+@pytest.mark.parametrize("name", ["tiny_pad", "ragged_sharp", "single_row", "mid_sharp", "2DRB_1"])
+def test_tf32x3_mode_vs_reference_golden(pkg, golden_dir, name):
+    """precision='tf32x3' (fp32 storage / attention / LayerNorm, nn.Linear layers as three-term tf32 products on the
+    tensor cores) against the reference's own vectors: between the fp32 path (<= 1e-4) and the fp16 path (<= 2e-2)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    layers = int(g["layers"])
+    model, _ = build(pkg, g["wseed"], layers, g["sharpen"], "tf32x3")
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    out = model(tokens, repr_layers=[layers], need_head_weights=True)
+    emb, atp = pkg.extract_features(out, model.vocab, layers)
+    e_emb = O.rel_err(emb, g["emb"])
+    e_atp = O.rel_err(atp, g["atp"]) if "atp" in g else float("nan")
+    print(f"[{name}/tf32x3] emb {e_emb:.3e} atp {e_atp:.3e}")
+    assert e_emb < TF32X3_TOL and not e_atp >= TF32X3_TOL
+    assert torch.isfinite(out["logits"]).all()
+
+
 def test_deep_msa_without_row_positions(pkg):
     """R > 1024 is rejected with the row-position embedding (model.py:354-359) and accepted without
     (BASELINE config 4 runs with embed_positions_msa=False); checked against the oracle at 2 layers."""

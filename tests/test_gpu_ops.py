@@ -136,6 +136,43 @@ def test_linear_residual(L, M, N, K, code):
     assert rel(out, ref) < (2e-5 if code == 0 else 1e-5)   # fp32 output in both modes
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(1, 768, 768, 0), (300, 2304, 768, 0), (1000, 3072, 768, 1), (257, 768, 3072, 2),
+                                       (70000, 768, 768, 2)])
+def test_linear_tf32_split(L, M, N, K, epi):
+    """The 'tf32x3' mode's tensor-core linear (three kind::tf32 MMAs on hi / lo operand halves) against float64 on the
+    SAME fp32 inputs, every epilogue, tails, q scale / row mask.  The operand split is exact to 2^-23; the remaining
+    error is the tensor core's truncating fp32 accumulation (a few 1e-6 norm-relative, ~10x the FFMA kernel's, 1000x
+    below the fp16 path's) -- hence a fast high-precision mode, not the <= 1e-4 whole-model parity path."""
+    x, W, bias = gen((M, K), 21, 2.0), gen((N, K), 22, 0.05), gen((N,), 23, 0.1)
+    mask = (torch.rand(M, generator=torch.Generator().manual_seed(4)) < 0.2).to(torch.uint8)
+    q_cols = 768 if N == 2304 else 0
+    xd, Wd, bd = x.cuda(), W.cuda(), bias.cuda()
+    resid = gen((M, N), 24)
+    out = resid.clone().cuda() if epi == 2 else torch.empty(M, N, device="cuda")
+    nb = L.lib.rnamsm_linear_tf32_scratch_bytes(M, N, K)
+    scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    md = mask.cuda()
+    L.check(L.lib.rnamsm_linear_tf32(L.ptr(xd), L.ptr(Wd), L.ptr(bd), M, N, K, epi, 0.37, q_cols, L.ptr(md) if q_cols else None,
+                                     L.ptr(out), L.ptr(scratch), nb, L.stream_ptr()))
+    ref = x.double() @ W.double().T + bias.double()
+    if epi == 0 and q_cols:
+        ref[:, :q_cols] *= 0.37
+        ref[mask.bool(), :q_cols] = 0
+    elif epi == 0:
+        pass
+    elif epi == 1:
+        ref = O.gelu_erf(ref)
+    else:
+        ref = resid.double() + ref
+    e = rel(out, ref)
+    # the FFMA kernel on the same inputs, for scale
+    out2 = resid.clone().cuda() if epi == 2 else torch.empty(M, N, device="cuda")
+    L.check(L.lib.rnamsm_linear(L.ptr(xd), L.ptr(Wd), L.ptr(bd), M, N, K, 0, epi, 0.37, q_cols, L.ptr(md) if q_cols else None,
+                                L.ptr(out2), L.stream_ptr()))
+    print(f"[tf32x3 {M}x{N}x{K} epi {epi}] err {e:.2e} (FFMA kernel {rel(out2, ref):.2e})")
+    assert e < (1.5e-5 if K <= 768 else 5e-5)       # grows with the length of the accumulation chain (K / 8 steps x 3)
+
+
 @pytest.mark.parametrize("M,K,tr", [(129, 768, None), (256, 768, None), (1000, 3072, (40, 25)), (3000, 768, (30, 100)),
                                     (40000, 768, None)])
 @pytest.mark.parametrize("code,ycode", [(2, 2), (1, 1), (2, 1)], ids=["f16", "bf16", "f16_to_bf16"])
