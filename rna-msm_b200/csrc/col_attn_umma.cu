@@ -233,6 +233,8 @@ col_attn_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 int launch_col_attn_ws_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,
                           cudaStream_t st);   // col_attn_ws.cu
+int launch_col_attn_fa_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,
+                          cudaStream_t st);   // col_attn_fa.cu
 
 // Dispatch: MSAs deeper than one 128-row query tile run the persistent warp-specialised kernel
 // (col_attn_ws.cu: two query tiles ping-pong per CTA); shallow ones (R <= 128) keep this
@@ -247,8 +249,14 @@ int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, int col_m
     forced = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'w' ? 2 : 0));
   }
   const bool use_ws = forced == 2 || (forced == 0 && R > 128);
-  return use_ws ? launch_col_attn_ws_16(qkv, R, C, H, fp16, col_major, pad, ctx, st)
-                : launch_col_attn_small_16(qkv, R, C, H, fp16, col_major, pad, ctx, st);
+  if (!use_ws) return launch_col_attn_small_16(qkv, R, C, H, fp16, col_major, pad, ctx, st);
+  static int impl = -1;                  // RNAMSM_COL_IMPL=fa: the 128-key-step kernel with P in tensor memory (col_attn_fa.cu)
+  if (impl < 0) {
+    const char* e = getenv("RNAMSM_COL_IMPL");
+    impl = (e && e[0] == 'f') ? 1 : 0;
+  }
+  return impl == 1 ? launch_col_attn_fa_16(qkv, R, C, H, fp16, col_major, pad, ctx, st)
+                   : launch_col_attn_ws_16(qkv, R, C, H, fp16, col_major, pad, ctx, st);
 }
 
 int launch_col_attn_small_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,

@@ -58,13 +58,17 @@ constexpr bool kPolyPairs = false;          // true: 25 % of the exponentials as
                                             // identical time (452 / 685 / 578 TF/s either way): the XU is not the limiter
 constexpr float kRescaleThreshold = 8.0f;   // log2 units: P stays <= 2^8, exact in fp16 / bf16 range
 
-template <int NT>
+// G = item groups per CTA: the NT tiles form G groups of NT / G tiles; a group shares one K/V ring and works
+// through its own sequence of items, so with G = 2 the two groups' item boundaries (Q reload, PV(last), O
+// read-out) fall at different times and each hides behind the other group's steps.  G = 1 is the production
+// configuration; G = 2 (RNAMSM_COL_GROUPS=2) is written but NOT yet measured or validated on hardware.
+template <int NT, int G = 1>
 struct Cfg {
   static constexpr int kQBufs = NT == 2 ? 2 : 1;        // Q double-buffered across items when smem allows
   static constexpr int kKvStages = NT == 2 ? 4 : 3;
   static constexpr int OFF_Q = 0;                        // [kQBufs][NT tiles]
-  static constexpr int OFF_KV = OFF_Q + kQBufs * NT * Q_BYTES;   // [stages][K | V]
-  static constexpr int OFF_P = OFF_KV + kKvStages * 2 * KV_BYTES;
+  static constexpr int OFF_KV = OFF_Q + kQBufs * NT * Q_BYTES;   // [G groups][stages][K | V]
+  static constexpr int OFF_P = OFF_KV + G * kKvStages * 2 * KV_BYTES;
   static constexpr int OFF_BAR = OFF_P + NT * P_BYTES;
   static constexpr int kSmem = OFF_BAR + 512 + 1024;
   static constexpr int kWarps = 4 + 4 * NT;              // 4 role warps + one softmax warpgroup per tile
@@ -112,43 +116,49 @@ __device__ __forceinline__ Item decode_item(int item, int nqb, int H) {
   return it;
 }
 
-template <int NT, bool kFp16>
-__global__ void __launch_bounds__(Cfg<NT>::kThreads, 1)
+template <int NT, bool kFp16, int G>
+__global__ void __launch_bounds__(Cfg<NT, G>::kThreads, 1)
 col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    const __grid_constant__ CUtensorMap tm_o, int R, int C, int H, int col_major, int n_items,
                    const uint8_t* __restrict__ pad) {
   constexpr int fp16 = kFp16 ? 1 : 0;
-  using K = Cfg<NT>;
+  using K = Cfg<NT, G>;
   constexpr int kKvStages = K::kKvStages;
+  constexpr int TG = NT / G;                    // tiles per item group
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
-  uint64_t* q_full = bars;                      // [2]
-  uint64_t* q_empty = bars + 2;                 // [2]
-  uint64_t* kv_full = bars + 4;                 // [4]
-  uint64_t* kv_empty = bars + 8;                // [4]
-  uint64_t* s_full = bars + 12;                 // [4] per tile
-  uint64_t* s_free = bars + 16;
-  uint64_t* p_full = bars + 20;
-  uint64_t* pv_done = bars + 24;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* q_full = bars;                      // [G][2]
+  uint64_t* q_empty = bars + 2 * G;             // [G][2]
+  uint64_t* kv_full = bars + 4 * G;             // [G][4]
+  uint64_t* kv_empty = bars + 8 * G;            // [G][4]
+  uint64_t* s_full = bars + 12 * G;             // [4] per tile
+  uint64_t* s_free = bars + 12 * G + 4;
+  uint64_t* p_full = bars + 12 * G + 8;
+  uint64_t* pv_done = bars + 12 * G + 12;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12 * G + 16);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int D = H * HD;
   const int nblk = (R + BKV - 1) / BKV;
-  const int nqb = (R + NT * BQ - 1) / (NT * BQ);
+  const int nqb = (R + TG * BQ - 1) / (TG * BQ);
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 2 * G; ++b) {
       mbar_init(&q_full[b], 1);
-      mbar_init(&q_empty[b], NT);               // one commit per MMA issuer
+      mbar_init(&q_empty[b], TG);               // one commit per MMA issuer of the group
     }
+    if (G == 2)
+      for (int b = 4; b < 8; ++b) {
+        mbar_init(&kv_full[b], 1);
+        mbar_init(&kv_empty[b], TG);
+      }
     for (int b = 0; b < 4; ++b) {
       mbar_init(&kv_full[b], 1);
-      mbar_init(&kv_empty[b], NT);              // one commit per MMA issuer
+      mbar_init(&kv_empty[b], TG);              // one commit per MMA issuer of the group
       mbar_init(&s_full[b], 1);
       mbar_init(&s_free[b], 4);
       mbar_init(&p_full[b], 4);
@@ -167,35 +177,36 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();                // RNAMSM_PDL=1: the prologue above overlapped the predecessor's tail
 
-  // Single-thread roles: TMA producer = warp 0 lane 0; MMA issuer of tile t = lane 0 of warp 1 + t for
-  // t < 3 and lane 1 of warp 0 for t = 3 (two roles on divergent lanes of warp 0: independent thread
-  // scheduling interleaves them, and it keeps the CTA at 20 warps = 96 registers per thread).
+  // Single-thread roles: TMA producer = warp 0 lane 0 (group 1's producer, G = 2: warp 1 lane 1); MMA issuer of
+  // tile t = lane 0 of warp 1 + t for t < 3 and lane 1 of warp 0 for t = 3 (two roles on divergent lanes of one
+  // warp: independent thread scheduling interleaves them, and it keeps the CTA at 20 warps = 96 registers per thread).
   const int mma_tile = (lane == 0 && warp >= 1 && warp <= 3 && warp - 1 < NT) ? warp - 1
                        : ((NT == 4 && warp == 0 && lane == 1) ? 3 : -1);
 
-  if (warp == 0 && lane == 0) {
-    // ================================ TMA producer ================================
+  if ((warp == 0 && lane == 0) || (G == 2 && warp == 1 && lane == 1)) {
+    // ================================ TMA producer (one per item group) ===========
     {
+      const int gr = (G == 2 && warp == 1) ? 1 : 0;
       int kv_stage = 0;
       uint32_t kv_phase = 0;
       int li = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
-        const Item it = decode_item<NT>(item, nqb, H);
+      for (int item = blockIdx.x * G + gr; item < n_items; item += gridDim.x * G, ++li) {
+        const Item it = decode_item<TG>(item, nqb, H);
         const int qb = K::kQBufs == 2 ? (li & 1) : 0;
         const int quse = K::kQBufs == 2 ? (li >> 1) : li;     // how many times this buffer was used before
-        mbar_wait_relaxed(&q_empty[qb], (quse & 1) ^ 1);
-        mbar_expect_tx(&q_full[qb], NT * Q_BYTES);
+        mbar_wait_relaxed(&q_empty[gr * 2 + qb], (quse & 1) ^ 1);
+        mbar_expect_tx(&q_full[gr * 2 + qb], TG * Q_BYTES);
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
-          tma_load_3d(smem + K::OFF_Q + (qb * NT + t) * Q_BYTES, &tm_q, &q_full[qb], it.h * HD,
-                      col_major ? it.i0 + t * BQ : it.c, col_major ? it.c : it.i0 + t * BQ);
+        for (int tl = 0; tl < TG; ++tl)
+          tma_load_3d(smem + K::OFF_Q + (qb * NT + gr * TG + tl) * Q_BYTES, &tm_q, &q_full[gr * 2 + qb], it.h * HD,
+                      col_major ? it.i0 + tl * BQ : it.c, col_major ? it.c : it.i0 + tl * BQ);
         for (int j = 0; j < nblk; ++j) {
-          mbar_wait_relaxed(&kv_empty[kv_stage], kv_phase ^ 1);
-          uint8_t* sk = smem + K::OFF_KV + kv_stage * 2 * KV_BYTES;
-          mbar_expect_tx(&kv_full[kv_stage], 2 * KV_BYTES);
-          tma_load_3d(sk, &tm_kv, &kv_full[kv_stage], D + it.h * HD, col_major ? j * BKV : it.c,
+          mbar_wait_relaxed(&kv_empty[gr * 4 + kv_stage], kv_phase ^ 1);
+          uint8_t* sk = smem + K::OFF_KV + (gr * kKvStages + kv_stage) * 2 * KV_BYTES;
+          mbar_expect_tx(&kv_full[gr * 4 + kv_stage], 2 * KV_BYTES);
+          tma_load_3d(sk, &tm_kv, &kv_full[gr * 4 + kv_stage], D + it.h * HD, col_major ? j * BKV : it.c,
                       col_major ? it.c : j * BKV);
-          tma_load_3d(sk + KV_BYTES, &tm_kv, &kv_full[kv_stage], 2 * D + it.h * HD, col_major ? j * BKV : it.c,
+          tma_load_3d(sk + KV_BYTES, &tm_kv, &kv_full[gr * 4 + kv_stage], 2 * D + it.h * HD, col_major ? j * BKV : it.c,
                       col_major ? it.c : j * BKV);
           if (++kv_stage == kKvStages) { kv_stage = 0; kv_phase ^= 1; }
         }
@@ -205,9 +216,11 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // ================================ MMA issuer of tile t =========================
     {
       const int t = mma_tile;
+      const int gr = t / TG;                                        // item group of this tile
       const uint32_t idesc_s = make_idesc_16(BQ, BKV, fp16, 0, 0);  // Q (K-major) x K (K-major)
       const uint32_t idesc_o = make_idesc_16(BQ, HD, fp16, 0, 1);   // P (K-major) x V (MN-major)
-      const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int first = (int)blockIdx.x * G + gr, stride = (int)gridDim.x * G;
+      const int my_items = (G == 1 || first < n_items) ? (n_items - first + stride - 1) / stride : 0;
       const long long total_steps = (long long)my_items * nblk;
       const uint32_t tmem_S = tmem_base + t * BKV, tmem_O = tmem_base + NT * BKV + t * HD;
       const uint32_t pa = smem_u32(smem + K::OFF_P + t * P_BYTES);
@@ -218,18 +231,18 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       auto issue_s = [&]() {
         const int qb = K::kQBufs == 2 ? (s_li & 1) : 0;
         const int quse = K::kQBufs == 2 ? (s_li >> 1) : s_li;
-        if (s_j == 0) mbar_wait_relaxed(&q_full[qb], quse & 1);
-        mbar_wait_relaxed(&kv_full[s_stage], s_phase);
+        if (s_j == 0) mbar_wait_relaxed(&q_full[gr * 2 + qb], quse & 1);
+        mbar_wait_relaxed(&kv_full[gr * 4 + s_stage], s_phase);
         if (gs > 0) mbar_wait_relaxed(&s_free[t], (uint32_t)((gs - 1) & 1));   // softmax t has S(gs-1) in registers
         tc_fence_after();
-        const uint32_t ka = smem_u32(smem + K::OFF_KV + s_stage * 2 * KV_BYTES);
+        const uint32_t ka = smem_u32(smem + K::OFF_KV + (gr * kKvStages + s_stage) * 2 * KV_BYTES);
         const uint32_t qa = smem_u32(smem + K::OFF_Q + (qb * NT + t) * Q_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_16(tmem_S, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024),
                   idesc_s, (uint32_t)(k != 0));
         umma_commit(&s_full[t]);
-        if (s_j == nblk - 1) umma_commit(&q_empty[qb]);            // this tile's Q fully consumed
+        if (s_j == nblk - 1) umma_commit(&q_empty[gr * 2 + qb]);   // this tile's Q fully consumed
         ++gs;
         if (++s_j == nblk) { s_j = 0; ++s_li; }
         if (++s_stage == kKvStages) { s_stage = 0; s_phase ^= 1; }
@@ -241,7 +254,7 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // tile, and PV(last) (which the softmax warps need for their epilogue) must not queue behind that wait
         const bool s_new_item = K::kQBufs == 1 && s_j == 0;      // (double-buffered Q is already there: keep S ahead)
         if (g + 1 < total_steps && !s_new_item) issue_s();
-        const uint32_t va = smem_u32(smem + K::OFF_KV + o_stage * 2 * KV_BYTES + KV_BYTES);
+        const uint32_t va = smem_u32(smem + K::OFF_KV + (gr * kKvStages + o_stage) * 2 * KV_BYTES + KV_BYTES);
         mbar_wait_relaxed(&p_full[t], (uint32_t)(g & 1));                  // P_t(g) in smem, O_t rescaled if needed
         tc_fence_after();
 #pragma unroll
@@ -249,7 +262,7 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           umma_16(tmem_O, make_smem_desc_sw128(pa + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 2048, 8192, 1024),
                   idesc_o, (uint32_t)((o_j | k) != 0));
         umma_commit(&pv_done[t]);
-        umma_commit(&kv_empty[o_stage]);                           // this tile is done with K_j and V_j
+        umma_commit(&kv_empty[gr * 4 + o_stage]);                  // this tile is done with K_j and V_j
         if (++o_j == nblk) o_j = 0;
         if (++o_stage == kKvStages) o_stage = 0;
         if (g + 1 < total_steps && s_new_item) issue_s();
@@ -258,6 +271,7 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   } else if (warp >= 4 && warp < 4 + 4 * NT) {
     // ================================ softmax warpgroups ==========================
     const int t = (warp - 4) >> 2;                 // tile
+    const int gr = t / TG, tl = t % TG;            // item group, tile inside the group's item
     const int quad = warp & 3;                     // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
@@ -266,8 +280,8 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     uint8_t* prow = smem + K::OFF_P + t * P_BYTES + row * 128;
     const float neg_masked = -10000.f;             // masked_fill value, modules.py:911-915
     long long g = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const Item it = decode_item<NT>(item, nqb, H);
+    for (int item = blockIdx.x * G + gr; item < n_items; item += gridDim.x * G) {
+      const Item it = decode_item<TG>(item, nqb, H);
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nblk; ++j, ++g) {
         const int j0 = j * BKV;
@@ -411,7 +425,7 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       fence_proxy_async_smem();     // staged rows -> visible to the TMA (async proxy)
       __syncwarp();
-      const int i_warp = it.i0 + t * BQ + quad * 32;           // first query row of this warp; rows >= R are clipped
+      const int i_warp = it.i0 + tl * BQ + quad * 32;          // first query row of this warp; rows >= R are clipped
       if (lane == 0 && i_warp < R) {
         tma_store_3d(&tm_o, smem + K::OFF_P + t * P_BYTES + quad * 32 * 128, it.h * HD, it.c, i_warp);
         bulk_commit();
@@ -426,24 +440,26 @@ col_attn_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, K::kTmemCols);
 }
 
-template <int NT, bool kFp16>
+template <int NT, bool kFp16, int G = 1>
 int launch_nt(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to, int R, int C, int H, int col_major,
               const uint8_t* pad, cudaStream_t st) {
-  using K = Cfg<NT>;
+  using K = Cfg<NT, G>;
+  static_assert(K::kSmem <= 227 * 1024, "column attention: shared memory budget");
+  constexpr int TG = NT / G;
   static bool attr_set = false;
   if (!attr_set) {
-    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_ws_kernel<NT, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmem));
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_ws_kernel<NT, kFp16, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmem));
     attr_set = true;
   }
-  const long long n_items = (long long)C * H * ((R + NT * BQ - 1) / (NT * BQ));
+  const long long n_items = (long long)C * H * ((R + TG * BQ - 1) / (TG * BQ));
   RNAMSM_REQUIRE(n_items < (1LL << 31), "col_attn_ws: too many work items");
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
-  const int grid = (int)std::min<long long>(n_items, sms);
+  const int grid = (int)std::min<long long>((n_items + G - 1) / G, sms);
   ProfScope prof(KC_COL_ATTN, st);
-  RNAMSM_CHECK_CUDA(launch_pdl(col_attn_ws_kernel<NT, kFp16>, dim3(grid), dim3(K::kThreads), K::kSmem, st, tq, tkv, to, R, C, H,
+  RNAMSM_CHECK_CUDA(launch_pdl(col_attn_ws_kernel<NT, kFp16, G>, dim3(grid), dim3(K::kThreads), K::kSmem, st, tq, tkv, to, R, C, H,
                                col_major, (int)n_items, pad));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
@@ -478,6 +494,15 @@ int launch_col_attn_ws_16(const void* qkv, int R, int C, int H, int fp16, int co
     const char* e = getenv("RNAMSM_COL_NT");
     forced = e ? atoi(e) : 0;
   }
+  // EXPERIMENTAL, off by default, not yet run on hardware: RNAMSM_COL_GROUPS=2 -> four tiles as two item groups
+  static int groups = -1;
+  if (groups < 0) {
+    const char* e = getenv("RNAMSM_COL_GROUPS");
+    groups = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  if (groups == 2)
+    return fp16 ? launch_nt<4, true, 2>(tq, tkv, to, R, C, H, col_major, pad, st)
+                : launch_nt<4, false, 2>(tq, tkv, to, R, C, H, col_major, pad, st);
   const int nt = forced == 2 || forced == 4 ? forced : (R > 2 * BQ ? 4 : 2);
   if (nt == 4)
     return fp16 ? launch_nt<4, true>(tq, tkv, to, R, C, H, col_major, pad, st)
