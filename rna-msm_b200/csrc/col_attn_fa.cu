@@ -21,14 +21,19 @@
 // does not collide with that.
 //
 //   warp 0 lane 0     TMA producer: Q tiles (double-buffered across items) and a K/V ring of 128-key stages
-//   warps 1, 2        MMA issuer of tile 0 / 1 (lane 0); warp 1 owns the TMEM allocation; warp 3 idle
-//   warps 4..11       softmax, one warpgroup per tile (thread = query row = TMEM lane): lazy rescaling (threshold 2^8),
+//   warps 1, 2        S issuer of tile 0 / 1 (lane 0); warp 1 owns the TMEM allocation
+//   warps 4, 5        PV issuer of tile 0 / 1 (lane 0); warps 3, 6, 7 idle (roles come in whole warpgroups for setmaxnreg)
+//   warps 8..15       softmax, one warpgroup per tile (thread = query row = TMEM lane): lazy rescaling (threshold 2^8),
 //                     packed fp32 pair arithmetic, optional polynomial 2^x on the FMA pipe for a share of the pairs
 #include <stdlib.h>
 
 #include "../../include/rnamsm_b200.h"
 #include "common.cuh"
 #include "launch.h"
+
+#ifndef RNAMSM_COL_WG
+#define RNAMSM_COL_WG 1
+#endif
 
 namespace rnamsm {
 
@@ -38,15 +43,19 @@ constexpr int NT = 2, BQ = 128, BKV = 128, HD = 64;
 constexpr int Q_BYTES = BQ * HD * 2;        // 16 KiB per tile
 constexpr int KV_BYTES = BKV * HD * 2;      // 16 KiB each for K and V
 constexpr int STG_BYTES = BQ * HD * 2;      // 16 KiB per tile: O rows staged for the TMA store
-constexpr int kKvStages = 4;
+constexpr int kKvStages = RNAMSM_COL_WG == 2 ? 3 : 4;   // (two warpgroups per tile: 2 KiB of row sums take the room of the 4th stage)
 constexpr int OFF_Q = 0;                                     // [2 item buffers][NT tiles]
 constexpr int OFF_KV = OFF_Q + 2 * NT * Q_BYTES;             // [stages][K | V]
 constexpr int OFF_STG = OFF_KV + kKvStages * 2 * KV_BYTES;   // [NT tiles]
-constexpr int OFF_BAR = OFF_STG + NT * STG_BYTES;
+constexpr int OFF_LSUM = OFF_STG + NT * STG_BYTES;            // [NT][2][BQ] fp32 partial row sums (kWG = 2)
+constexpr int OFF_BAR = OFF_LSUM + (RNAMSM_COL_WG == 2 ? NT * 2 * BQ * 4 : 0);
 constexpr int kSmem = OFF_BAR + 512 + 1024;
-constexpr int kWarps = 4 + 4 * NT;
-constexpr int kThreads = 32 * kWarps;                        // 384 threads -> up to 168 registers each
-constexpr int kRoleRegs = 40, kSoftmaxRegs = 224;            // setmaxnreg: 128 x 40 + 256 x 224 = 62464 <= 64512 allocated at launch
+constexpr int kWG = RNAMSM_COL_WG;                           // softmax warpgroups per tile (1: a thread owns 128 keys of a step, 2: 64)
+constexpr int CW = BKV / kWG;                                // key columns per softmax thread and step
+constexpr int kRoleWarps = 8;                                // two warpgroups of single-thread roles (3 warps idle)
+constexpr int kWarps = kRoleWarps + 4 * NT * kWG;
+constexpr int kThreads = 32 * kWarps;                        // 512 (kWG = 1) or 768 threads
+constexpr int kRoleRegs = kWG == 1 ? 40 : 32, kSoftmaxRegs = kWG == 1 ? 216 : 104;   // setmaxnreg; kWG = 1: 256 x 40 + 256 x 216 = 65536 (launch 512 x 128); kWG = 2: 256 x 32 + 512 x 104 = 61440 = launch 768 x 80
 constexpr int kTmemCols = 512;
 constexpr int TM_S = 0, TM_P = 128, TM_O = 192, TM_TILE = 256;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -58,6 +67,8 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Orders a volatile asm (a barrier probe) behind the computation of v without emitting an instruction.
+__device__ __forceinline__ void anchor_after(float v) { asm volatile("" ::"f"(v) : "memory"); }
 
 // 2^x for a packed pair on the FMA / ALU pipes instead of the XU: x = n + f by the 1.5 * 2^23 magic add, degree-3
 // minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, below the 16-bit rounding of P), n added
@@ -82,6 +93,19 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x, float& r0, float& r1) {
 
 struct Item { int c, h, i0; };
 
+// Debug timeline (RNAMSM_COL_TRACE=<file>): CTA 0 logs clock64() at the hand-over points of its first steps, one row per
+// role thread; dumped by the launcher.  Compiled into a separate instantiation only.
+constexpr int kTraceRoles = 7, kTraceLen = 512;
+__device__ long long g_trace[kTraceRoles][kTraceLen];
+template <bool kTrace>
+struct Tracer {
+  int role, n;
+  __device__ __forceinline__ Tracer(int r) : role(r), n(0) {}
+  __device__ __forceinline__ void log(int code) {
+    if (kTrace && blockIdx.x == 0 && n < kTraceLen) g_trace[role][n++] = (clock64() << 4) | code;
+  }
+};
+
 __device__ __forceinline__ Item decode_item(int item, int nqb, int H) {
   Item it;
   it.i0 = (item % nqb) * (NT * BQ);
@@ -93,11 +117,11 @@ __device__ __forceinline__ Item decode_item(int item, int nqb, int H) {
 
 // kPoly: 0 = every exponential on the XU; n > 0 = the second pair of every n-th group of four keys on the FMA pipe
 // (exp2_poly2): 1 -> 50 % of the exponentials, 2 -> 25 %, 4 -> 12.5 %
-template <bool kFp16, int kPoly>
+template <bool kFp16, int kPoly, bool kTrace>
 __global__ void __launch_bounds__(kThreads, 1)
 col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    const __grid_constant__ CUtensorMap tm_o, int R, int C, int H, int col_major, int n_items,
-                   const uint8_t* __restrict__ pad) {
+                   const uint8_t* __restrict__ pad, int stagger, int tight) {
   constexpr int fp16 = kFp16 ? 1 : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -126,8 +150,8 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], NT);               // one commit per MMA issuer
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_free[b], 4);
-      mbar_init(&p_full[b], 4);
+      mbar_init(&s_free[b], 4 * kWG);
+      mbar_init(&p_full[b], 4 * kWG);
       mbar_init(&pv_done[b], 1);
     }
     for (int b = 0; b < 4; ++b) {
@@ -147,13 +171,14 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp < 4) {
+  if (warp < kRoleWarps) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRoleRegs));
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
     int kv_stage = 0;
     uint32_t kv_phase = 0;
     int li = 0;
+    Tracer<kTrace> tr(0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
       const Item it = decode_item(item, nqb, H);
       const int qb = li & 1, quse = li >> 1;
@@ -165,6 +190,7 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     col_major ? it.i0 + t * BQ : it.c, col_major ? it.c : it.i0 + t * BQ);
       for (int j = 0; j < nblk; ++j) {
         mbar_wait_relaxed(&kv_empty[kv_stage], kv_phase ^ 1);
+        tr.log(1);
         uint8_t* sk = smem + OFF_KV + kv_stage * 2 * KV_BYTES;
         mbar_expect_tx(&kv_full[kv_stage], 2 * KV_BYTES);
         tma_load_3d(sk, &tm_kv, &kv_full[kv_stage], D + it.h * HD, col_major ? j * BKV : it.c, col_major ? it.c : j * BKV);
@@ -174,78 +200,114 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else if ((warp == 1 || warp == 2) && lane == 0) {
-    // ================================ MMA issuer of tile t =========================
+    // ================================ S issuer of tile t ===========================
+    // S and PV have separate issuing threads: one thread doing both (12 instructions per step, each behind ~15 scalar
+    // instructions of descriptor arithmetic and the barrier round trips) was the slowest stage of the pipeline -- ncu:
+    // 46 % of the steps found S not ready, and with S moved ahead of PV the wait moved to PV.
     const int t = warp - 1;
     const uint32_t idesc_s = make_idesc_16(BQ, BKV, fp16, 0, 0);  // Q (K-major, smem) x K (K-major, smem), N = 128 keys
+    const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t tmem_S = tmem_base + t * TM_TILE + TM_S;
+    int s_stage = 0;
+    uint32_t s_phase = 0;
+    long long gs = 0;
+    Tracer<kTrace> tr(1 + t);
+    for (int li = 0; li < my_items; ++li) {
+      const int qb = li & 1, quse = li >> 1;
+      mbar_wait_relaxed(&q_full[qb], quse & 1);
+      const uint32_t qa = smem_u32(smem + OFF_Q + (qb * NT + t) * Q_BYTES);
+      for (int j = 0; j < nblk; ++j, ++gs) {
+        mbar_wait_relaxed(&kv_full[s_stage], s_phase);
+        tr.log(1);                                                           // K/V stage landed
+        if (gs > 0) {                                                        // softmax t holds S(gs-1) in registers
+          if (tight) mbar_wait_quiet(&s_free[t], (uint32_t)((gs - 1) & 1));
+          else mbar_wait_relaxed(&s_free[t], (uint32_t)((gs - 1) & 1));
+        }
+        tr.log(2);                                                           // S columns free
+        tc_fence_after();
+        const uint32_t ka = smem_u32(smem + OFF_KV + s_stage * 2 * KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_16(tmem_S, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s,
+                  (uint32_t)(k != 0));
+        umma_commit(&s_full[t]);
+        tr.log(3);                                                           // S issued
+        if (j == nblk - 1) umma_commit(&q_empty[qb]);            // this tile's Q fully consumed
+        if (++s_stage == kKvStages) { s_stage = 0; s_phase ^= 1; }
+      }
+    }
+  } else if ((warp == 4 || warp == 5) && lane == 0) {
+    // ================================ PV issuer of tile t ==========================
+    const int t = warp - 4;
     const uint32_t idesc_o = make_idesc_16(BQ, HD, fp16, 0, 1);   // P (TMEM) x V (MN-major, smem)
     const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const long long total_steps = (long long)my_items * nblk;
-    const uint32_t tmem_S = tmem_base + t * TM_TILE + TM_S, tmem_P = tmem_base + t * TM_TILE + TM_P,
-                   tmem_O = tmem_base + t * TM_TILE + TM_O;
-    long long gs = 0;                        // cursor of the S issue (one step ahead of the PV issue)
-    int s_li = 0, s_j = 0, s_stage = 0;
-    uint32_t s_phase = 0;
-    auto issue_s = [&]() {
-      const int qb = s_li & 1, quse = s_li >> 1;
-      if (s_j == 0) mbar_wait_relaxed(&q_full[qb], quse & 1);
-      mbar_wait_relaxed(&kv_full[s_stage], s_phase);
-      if (gs > 0) mbar_wait_relaxed(&s_free[t], (uint32_t)((gs - 1) & 1));   // softmax t holds S(gs-1) in registers
-      tc_fence_after();
-      const uint32_t ka = smem_u32(smem + OFF_KV + s_stage * 2 * KV_BYTES);
-      const uint32_t qa = smem_u32(smem + OFF_Q + (qb * NT + t) * Q_BYTES);
-#pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        umma_16(tmem_S, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s,
-                (uint32_t)(k != 0));
-      umma_commit(&s_full[t]);
-      if (s_j == nblk - 1) umma_commit(&q_empty[qb]);            // this tile's Q fully consumed
-      ++gs;
-      if (++s_j == nblk) { s_j = 0; ++s_li; }
-      if (++s_stage == kKvStages) { s_stage = 0; s_phase ^= 1; }
-    };
+    const uint32_t tmem_P = tmem_base + t * TM_TILE + TM_P, tmem_O = tmem_base + t * TM_TILE + TM_O;
     int o_j = 0, o_stage = 0;
-    if (total_steps > 0) issue_s();
+    uint32_t o_phase = 0;
+    Tracer<kTrace> tr(3 + t);
     for (long long g = 0; g < total_steps; ++g) {
-      if (g + 1 < total_steps) issue_s();
       const uint32_t va = smem_u32(smem + OFF_KV + o_stage * 2 * KV_BYTES + KV_BYTES);
-      mbar_wait_relaxed(&p_full[t], (uint32_t)(g & 1));          // P_t(g) in TMEM, O_t rescaled if needed
+      mbar_wait_relaxed(&kv_full[o_stage], o_phase);             // (complete long ago: this thread's own acquire of V)
+      tr.log(2);
+      if (tight) mbar_wait_quiet(&p_full[t], (uint32_t)(g & 1));   // P_t(g) in TMEM, O_t rescaled if needed
+      else mbar_wait_relaxed(&p_full[t], (uint32_t)(g & 1));
+      tr.log(1);                                                 // P seen
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < BKV / 16; ++k)                         // 16 keys = 8 packed TMEM columns per instruction
         umma_16_ts(tmem_O, tmem_P + k * 8, make_smem_desc_sw128(va + k * 2048, 8192, 1024), idesc_o,
                    (uint32_t)((o_j | k) != 0));
       umma_commit(&pv_done[t]);
+      tr.log(3);                                                 // PV issued
       umma_commit(&kv_empty[o_stage]);                           // this tile is done with K_j and V_j
       if (++o_j == nblk) o_j = 0;
-      if (++o_stage == kKvStages) o_stage = 0;
+      if (++o_stage == kKvStages) { o_stage = 0; o_phase ^= 1; }
     }
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSoftmaxRegs));
     // ================================ softmax warpgroups ==========================
-    const int t = (warp - 4) >> 2;                 // tile
+    // kWG warpgroups per tile: warpgroup `half` owns key columns [half * CW, half * CW + CW) of every step; a thread is one
+    // query row (TMEM lane) restricted to those columns.
+    const int sw = warp - kRoleWarps;
+    const int t = sw / (4 * kWG);                  // tile
+    const int half = (sw >> 2) % kWG;              // which CW-key part of the 128 keys of a step
     const int quad = warp & 3;                     // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const uint32_t tmem_S = tmem_base + t * TM_TILE + TM_S + lane_off;
-    const uint32_t tmem_P = tmem_base + t * TM_TILE + TM_P + lane_off;
+    const uint32_t tmem_P = tmem_base + t * TM_TILE + TM_P + lane_off + half * (CW / 2);
     const uint32_t tmem_O = tmem_base + t * TM_TILE + TM_O + lane_off;
     uint8_t* srow = smem + OFF_STG + t * STG_BYTES + row * 128;
+    float* lsum = reinterpret_cast<float*>(smem + OFF_LSUM) + (t * 2) * BQ + row;   // [tile][half][row] partial row sums
+    const int pair_bar = 1 + t * 4 + quad;         // named barrier of the kWG warps that share these 32 rows
+    const uint32_t b_s_full = smem_u32(&s_full[t]), b_s_free = smem_u32(&s_free[t]), b_p_full = smem_u32(&p_full[t]),
+                   b_pv_done = smem_u32(&pv_done[t]);
     const float neg_masked = -10000.f;             // masked_fill value, modules.py:911-915
     long long g = 0;
     // The read-out of an item's O (its "epilogue") is deferred into the first step of the NEXT item, after that step's
     // exponentials: PV(last) of the finished item completes behind them instead of being waited for (ncu: 13 probes
     // per item on that wait = 6 % of the softmax warps' time at R = 1024, more for shallower MSAs).
     bool have_prev = false, s_ok = false;
+    Tracer<kTrace> tr(half == 0 && quad == 0 && lane == 0 ? 5 + t : -1);
     Item prev_it{0, 0, 0};
-    float prev_inv = 0.f;
-    auto read_out = [&](const Item& pit, float inv) {
+    float prev_l = 0.f;
+    auto read_out = [&](const Item& pit, float l_part) {
       // 16-bit rows staged in shared memory (SWIZZLE_128B pattern of the store's tensor map), one asynchronous TMA
-      // store per warp
-      if (lane == 0) bulk_wait_read0();             // the staged rows of the item before have been read by their store
-      __syncwarp();
+      // store per 32 rows.  With two warpgroups per tile each normalises and stages its own 32 of the 64 output columns;
+      // the row sums meet through shared memory.
+      if (half == 0 && lane == 0) bulk_wait_read0();   // the staged rows of the item before have been read by their store
+      float l_tot = l_part;
+      if (kWG == 2) {
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner's partial sum written, staging free
+        l_tot += lsum[(half ^ 1) * BQ];
+      } else {
+        __syncwarp();
+      }
+      const float inv = 1.f / l_tot;
 #pragma unroll 1
-      for (int hlf = 0; hlf < 2; ++hlf) {
+      for (int hlf = (kWG == 2 ? half : 0); hlf < (kWG == 2 ? half + 1 : 2); ++hlf) {
         uint32_t ov[32];
         tmem_ld_32x32(tmem_O + hlf * 32, ov);
         tmem_ld_wait();
@@ -267,34 +329,75 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
       }
       fence_proxy_async_smem();     // staged rows -> visible to the TMA (async proxy)
-      __syncwarp();
+      if (kWG == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // both column halves staged
+      else __syncwarp();
       const int i_warp = pit.i0 + t * BQ + quad * 32;          // first query row of this warp; rows >= R are clipped
-      if (lane == 0 && i_warp < R) {
+      if (half == 0 && lane == 0 && i_warp < R) {
         tma_store_3d(&tm_o, smem + OFF_STG + t * STG_BYTES + quad * 32 * 128, pit.h * HD, pit.c, i_warp);
         bulk_commit();
       }
     };
+    // (kWG == 1) The two tiles' warps share each sub-partition's XU; tile 1 may start late once (kStagger cycles).
+    if (stagger > 0 && t == 1) {
+      const long long t_start = clock64();
+      while (clock64() - t_start < stagger) {}
+    }
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(item, nqb, H);
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nblk; ++j, ++g) {
-        const int j0 = j * BKV;
-        if (!s_ok) mbar_wait_quiet(&s_full[t], (uint32_t)(g & 1));   // (probed at the end of the previous step)
+        const int j0 = j * BKV + half * CW;        // first key of this thread's columns
+        if (!s_ok) mbar_wait_quiet_u32(b_s_full, (uint32_t)(g & 1));   // (probed inside the previous step)
         tc_fence_after();
-        uint32_t sv[4][32];
-        tmem_ld_32x32(tmem_S, sv[0]);
-        tmem_ld_32x32(tmem_S + 32, sv[1]);
-        tmem_ld_32x32(tmem_S + 64, sv[2]);
-        tmem_ld_32x32(tmem_S + 96, sv[3]);
-        tmem_ld_wait();
+        if (tr.role >= 0) tr.log(s_ok ? 1 : 2);                  // S ready (1: the early probe had seen it)
+        uint32_t sv[CW / 32][32];
+        float mx_other = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < CW / 32; ++q) tmem_ld_32x32(tmem_S + half * CW + q * 32, sv[q]);
+        if (kWG == 2) {
+          // the row maximum needs all 128 logits: the other warpgroup's 64 columns are read as well (tensor-memory reads
+          // are cheap: 8 KiB per warp in ~35 cycles), only for the maximum -- identical arithmetic in both warpgroups, so
+          // both take the same rescaling decisions without talking to each other
+          const bool slow = pad != nullptr || j * BKV + BKV > R;
+          const int jo = j * BKV + (half ^ 1) * CW;
+#pragma unroll 1
+          for (int q = 0; q < CW / 32; ++q) {
+            uint32_t ot[32];
+            tmem_ld_32x32(tmem_S + (half ^ 1) * CW + q * 32, ot);
+            tmem_ld_wait();
+            uint32_t mbits = 0;
+            if (slow && pad != nullptr) {
+              const int jk = jo + q * 32 + lane;
+              mbits = __ballot_sync(0xffffffffu, jk < R && pad[(size_t)jk * C + it.c] != 0);
+            }
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              float v0 = __uint_as_float(ot[e]), v1 = __uint_as_float(ot[e + 1]);
+              if (slow) {
+                if ((mbits >> e) & 1u) v0 = neg_masked;
+                if ((mbits >> (e + 1)) & 1u) v1 = neg_masked;
+                if (jo + q * 32 + e >= R) v0 = -INFINITY;
+                if (jo + q * 32 + e + 1 >= R) v1 = -INFINITY;
+              }
+              m0 = fmaxf(m0, v0);
+              m1 = fmaxf(m1, v1);
+            }
+            mx_other = fmaxf(mx_other, fmaxf(m0, m1));
+          }
+        } else {
+          tmem_ld_wait();
+        }
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[t]);    // S columns may be overwritten by the next step's S
+        if (kWG == 2) __syncwarp();
+        else __syncwarp();
+        if (tr.role >= 0) tr.log(3);                             // S in registers
+        if (lane == 0) mbar_arrive_u32(b_s_free);   // S columns may be overwritten by the next step's S
 
-        if (pad != nullptr || j0 + BKV > R) {      // warp-uniform slow path: key masks
+        if (pad != nullptr || j * BKV + BKV > R) {               // warp-uniform slow path: key masks
           const int n_valid = R - j0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < CW / 32; ++q) {
             uint32_t mbits = 0;
             if (pad != nullptr) {
               const int jk = j0 + q * 32 + lane;
@@ -309,13 +412,16 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             }
           }
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        float mx0 = mx_other, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          mx0 = fmaxf(mx0, __uint_as_float(sv[0][e]));
-          mx1 = fmaxf(mx1, __uint_as_float(sv[1][e]));
-          mx2 = fmaxf(mx2, __uint_as_float(sv[2][e]));
-          mx3 = fmaxf(mx3, __uint_as_float(sv[3][e]));
+        for (int q = 0; q < CW / 32; ++q) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(sv[q][e]));
+            mx1 = fmaxf(mx1, __uint_as_float(sv[q][e + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(sv[q][e + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(sv[q][e + 3]));
+          }
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * kLog2e;   // log2 domain; finite (>= 1 real key)
         // lazy rescale: keep the old reference unless the max grew by more than the threshold
@@ -327,15 +433,13 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           l_run *= factor;
         }
         const bool rescale = (j > 0) && __any_sync(0xffffffffu, grow);
-        // probe "PV(g-1) done" now and look at the answer after the exponentials: a try_wait costs ~100 cycles of
-        // latency even when the phase completed long ago
-        const bool pv_ok = g > 0 ? mbar_try_wait(&pv_done[t], (uint32_t)((g - 1) & 1)) : true;
-        // exponentials on packed fp32 pairs; the 16-bit P words (keys 2w, 2w+1 -> word w) overwrite sv[0], sv[1]
+        bool pv_ok = g == 0;
+        // exponentials on packed fp32 pairs; the 16-bit P words (keys 2w, 2w+1 -> word w) overwrite sv[0] (and sv[1])
         // behind the read position
         const uint64_t c_l2e = f32x2_pack(kLog2e, kLog2e), c_negm = f32x2_pack(-m_ref, -m_ref);
         uint64_t acc0 = f32x2_pack(0.f, 0.f), acc1 = acc0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < CW / 32; ++q) {
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             const uint64_t x0 = f32x2_fma(f32x2_pack(__uint_as_float(sv[q][e]), __uint_as_float(sv[q][e + 1])), c_l2e, c_negm);
@@ -343,6 +447,13 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             float a0, a1, a2, a3;
             f32x2_unpack(x0, a0, a1);
             a0 = ex2(a0); a1 = ex2(a1);
+            if (q == CW / 32 - 1 && e == 16) {
+              // probe "PV(g-1) done" seven eighths through (a test_wait is non-blocking; its ~100 cycles of latency pass
+              // behind the last exponentials; the in-kernel timeline puts PV(g-1)'s completion ~1300 cycles after P(g-1)
+              // was handed over: a barrier hand-over between threads costs ~350 cycles each way)
+              anchor_after(a1);
+              if (g > 0) pv_ok = mbar_test_wait_u32(b_pv_done, (uint32_t)((g - 1) & 1));
+            }
             constexpr int kP = kPoly > 0 ? kPoly : 1;
             if (kPoly > 0 && (((q * 32 + e) >> 2) % kP) == kP - 1) {
               exp2_poly2(x1, a2, a3);
@@ -352,7 +463,7 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             }
             acc0 = f32x2_add(acc0, f32x2_pack(a0, a1));
             acc1 = f32x2_add(acc1, f32x2_pack(a2, a3));
-            const int w = (q * 32 + e) >> 1;                 // P word index 0..63
+            const int w = (q * 32 + e) >> 1;                 // P word index inside this thread's columns
             sv[w >> 5][w & 31] = kFp16 ? pack_f16(a0, a1) : pack_bf16(a0, a1);
             sv[(w + 1) >> 5][(w + 1) & 31] = kFp16 ? pack_f16(a2, a3) : pack_bf16(a2, a3);
           }
@@ -363,13 +474,16 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           f32x2_unpack(acc1, s2, s3);
           l_run += (s0 + s1) + (s2 + s3);
         }
-        if (!pv_ok) mbar_wait_quiet(&pv_done[t], (uint32_t)((g - 1) & 1));   // PV(g-1) done: P columns free, O_t stable
+        s_ok = mbar_test_wait_u32(b_s_full, (uint32_t)((g + 1) & 1));   // next step's S; the answer is used ~400 cycles on
+        if (tr.role >= 0) tr.log(pv_ok ? 4 : 5);                 // exponentials done (4: the probe had seen PV(g-1) done)
+        if (!pv_ok) mbar_wait_quiet_u32(b_pv_done, (uint32_t)((g - 1) & 1));   // PV(g-1) done: P columns free, O_t stable
         tc_fence_after();
-        if (j == 0 && have_prev) read_out(prev_it, prev_inv);   // the finished item's O, before PV(g) overwrites it
+        if (tr.role >= 0) tr.log(6);                             // PV(g-1) done
+        if (j == 0 && have_prev) read_out(prev_it, prev_l);     // the finished item's O, before PV(g) overwrites it
         if (rescale) {                              // warp-uniform; rare once the max has settled
           uint32_t ov[32];
 #pragma unroll 1
-          for (int hlf = 0; hlf < 2; ++hlf) {
+          for (int hlf = (kWG == 2 ? half : 0); hlf < (kWG == 2 ? half + 1 : 2); ++hlf) {
             tmem_ld_32x32(tmem_O + hlf * 32, ov);
             tmem_ld_wait();
 #pragma unroll
@@ -377,38 +491,52 @@ col_attn_fa_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             tmem_st_32x32(tmem_O + hlf * 32, ov);
           }
         }
-        tmem_st_32x32(tmem_P, sv[0]);               // P(g): 128 keys -> 64 packed columns, the A operand of P V
-        tmem_st_32x32(tmem_P + 32, sv[1]);
-        s_ok = mbar_try_wait(&s_full[t], (uint32_t)((g + 1) & 1));   // next step's S: normally complete by now
+#pragma unroll
+        for (int q = 0; q < CW / 64; ++q) tmem_st_32x32(tmem_P + q * 32, sv[q]);   // P(g): two keys per column, A operand of P V
         tmem_st_wait();
         tc_fence_before();                          // our tcgen05.ld / st precede the MMA that follows the barrier
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (tr.role >= 0) tr.log(7);                             // P handed over
+        if (lane == 0) mbar_arrive_u32(b_p_full);
       }
       prev_it = it;
-      prev_inv = 1.f / l_run;
+      prev_l = l_run;
+      if (kWG == 2) lsum[half * BQ] = l_run;        // read by the partner warpgroup behind the first barrier of read_out
       have_prev = true;
     }
     if (have_prev) {                                // the last item of this CTA
-      mbar_wait_quiet(&pv_done[t], (uint32_t)((g - 1) & 1));
+      mbar_wait_quiet_u32(b_pv_done, (uint32_t)((g - 1) & 1));
       tc_fence_after();
-      read_out(prev_it, prev_inv);
+      read_out(prev_it, prev_l);
     }
     tc_fence_before();
   }
 
-  if (warp >= 4 && lane == 0) bulk_wait_all0();   // the last items' TMA stores have left shared memory
+  if (warp >= kRoleWarps && lane == 0) bulk_wait_all0();   // the last items' TMA stores have left shared memory
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <bool kFp16, int kPoly>
+// Experiment knobs (defaults = the measured best): RNAMSM_COL_STAGGER=<cycles> delays tile 1's softmax warps once,
+// RNAMSM_COL_TIGHT=0 lets the S / PV issuing threads sleep on their barriers instead of probing them back to back.
+int knob_stagger() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RNAMSM_COL_STAGGER"); v = e ? atoi(e) : 0; }
+  return v;
+}
+int knob_tight() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RNAMSM_COL_TIGHT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+template <bool kFp16, int kPoly, bool kTrace = false>
 int launch_fa(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to, int R, int C, int H, int col_major,
               const uint8_t* pad, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_fa_kernel<kFp16, kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(col_attn_fa_kernel<kFp16, kPoly, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   const long long n_items = (long long)C * H * ((R + NT * BQ - 1) / (NT * BQ));
@@ -419,10 +547,21 @@ int launch_fa(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& 
   if (sms <= 0) sms = 148;
   const int grid = (int)std::min<long long>(n_items, sms);
   ProfScope prof(KC_COL_ATTN, st);
-  RNAMSM_CHECK_CUDA(launch_pdl(col_attn_fa_kernel<kFp16, kPoly>, dim3(grid), dim3(kThreads), kSmem, st, tq, tkv, to, R, C, H,
-                               col_major, (int)n_items, pad));
+  RNAMSM_CHECK_CUDA(launch_pdl(col_attn_fa_kernel<kFp16, kPoly, kTrace>, dim3(grid), dim3(kThreads), kSmem, st, tq, tkv, to, R, C, H,
+                               col_major, (int)n_items, pad, knob_stagger(), knob_tight()));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
+  if (kTrace) {
+    static long long h[kTraceRoles][kTraceLen];
+    RNAMSM_CHECK_CUDA(cudaStreamSynchronize(st));
+    RNAMSM_CHECK_CUDA(cudaMemcpyFromSymbol(h, g_trace, sizeof(h)));
+    if (FILE* f = fopen(getenv("RNAMSM_COL_TRACE"), "w")) {
+      static const char* names[kTraceRoles] = {"tma", "s0", "s1", "pv0", "pv1", "softmax0", "softmax1"};
+      for (int r = 0; r < kTraceRoles; ++r)
+        for (int i = 0; i < kTraceLen && h[r][i] != 0; ++i) fprintf(f, "%s %lld %d\n", names[r], h[r][i] >> 4, (int)(h[r][i] & 15));
+      fclose(f);
+    }
+  }
   return 0;
 }
 
@@ -452,6 +591,7 @@ int launch_col_attn_fa_16(const void* qkv, int R, int C, int H, int fp16, int co
     const char* e = getenv("RNAMSM_COL_POLY");
     poly = e ? atoi(e) : 0;
   }
+  if (fp16 && getenv("RNAMSM_COL_TRACE")) return launch_fa<true, 0, true>(tq, tkv, to, R, C, H, col_major, pad, st);
   if (poly == 4)
     return fp16 ? launch_fa<true, 4>(tq, tkv, to, R, C, H, col_major, pad, st)
                 : launch_fa<false, 4>(tq, tkv, to, R, C, H, col_major, pad, st);

@@ -250,10 +250,10 @@ int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, int col_m
   }
   const bool use_ws = forced == 2 || (forced == 0 && R > 128);
   if (!use_ws) return launch_col_attn_small_16(qkv, R, C, H, fp16, col_major, pad, ctx, st);
-  static int impl = -1;                  // RNAMSM_COL_IMPL=fa: the 128-key-step kernel with P in tensor memory (col_attn_fa.cu)
-  if (impl < 0) {
+  static int impl = -1;                  // default: the 128-key-step kernel with P in tensor memory (col_attn_fa.cu);
+  if (impl < 0) {                        // RNAMSM_COL_IMPL=ws keeps the round-1 four-tile / 64-key kernel (col_attn_ws.cu)
     const char* e = getenv("RNAMSM_COL_IMPL");
-    impl = (e && e[0] == 'f') ? 1 : 0;
+    impl = (e && e[0] == 'w') ? 0 : 1;
   }
   return impl == 1 ? launch_col_attn_fa_16(qkv, R, C, H, fp16, col_major, pad, ctx, st)
                    : launch_col_attn_ws_16(qkv, R, C, H, fp16, col_major, pad, ctx, st);

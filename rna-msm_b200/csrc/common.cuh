@@ -122,6 +122,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same on a precomputed shared-memory address (the generic -> shared conversion of a pointer is re-derived from
+// %cluster_ctaid at every use otherwise: measurable in per-step barrier traffic).
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Non-blocking probe (try_wait may suspend the warp for a while when the phase is still open: measured, a probe issued
+// early inside the softmax step cost 21 % of the kernel).
+__device__ __forceinline__ bool mbar_test_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_quiet_u32(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_u32(bar, parity))
+    if (++spins > (1u << 26)) __trap();
+}
+
 // Same bound, no message: for waits inside register-tight loops (the printf call site costs live registers).
 __device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
