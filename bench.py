@@ -108,6 +108,14 @@ def flops_breakdown(R, C):
     }
 
 
+def class_flops(R, C):
+    """flops_breakdown keyed by the library's timing classes: short alignments (C <= 128) run tied logits + softmax + AV
+    as ONE launch (row_attn_short.cu), whose class carries both terms."""
+    fl = flops_breakdown(R, C)
+    fl["row_attn_short"] = fl["row_logits"] + fl["row_av"]
+    return fl
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -370,19 +378,21 @@ def run_secondary(args, pkg, _lib, world, rank, peaks):
             torch.cuda.synchronize()
             prof = _lib.profile_collect()
             _lib.profile_enable(False)
-            fl = flops_breakdown(R, C)
+            fl = class_flops(R, C)
             res["class_tflops"] = {k: round(fl[k] * n_steps / (prof[k][0] * 1e-3) / 1e12, 1) for k in fl if prof[k][0] > 0}
             tot = sum(v[0] for v in prof.values())
             res["class_time_share"] = {k: round(v[0] / tot, 4) for k, v in prof.items() if v[1]}
-            t_tied = prof["row_logits"][0] + prof["row_av"][0]
+            t_short = prof.get("row_attn_short", (0.0, 0))[0]   # one launch does logits + softmax + AV when C <= 128
+            t_tied = prof["row_logits"][0] + prof["row_av"][0] + t_short
             tied = (fl["row_logits"] + fl["row_av"]) * n_steps / (t_tied * 1e-3) / 1e12
             tied_sm = (fl["row_logits"] + fl["row_av"]) * n_steps / ((t_tied + prof["row_softmax"][0]) * 1e-3) / 1e12
             res["tied_row_attention"] = {
                 "tflops": round(tied, 1), "frac_of_bf16_sustained": round(tied / peaks["bf16_sustained"], 4),
                 "frac_of_bf16_burst": round(tied / peaks["bf16_burst"], 4),
                 "tflops_incl_softmax_pass": round(tied_sm, 1),
-                "what": "tied logits (umma_gemm_kernel<TIED>) + AV (umma_gemm_kernel<AV>): 4 R C^2 D flops per layer over "
-                        "their live CUDA-event time inside the forward"}
+                "what": ("row_attn_short_kernel (logits + softmax + AV in one launch, C <= 128)" if t_short > 0 else
+                         "tied logits (umma_gemm_kernel<TIED>) + AV (umma_gemm_kernel<AV>)") +
+                        ": 4 R C^2 D flops per layer over their live CUDA-event time inside the forward"}
         del tok_dev, atp_host, emb_host
         return res
 
@@ -661,10 +671,10 @@ def run_ours(args):
         if farm:                                        # this rank's MSAs
             fl = {}
             for c in my_C:
-                for k, v in flops_breakdown(R, c).items():
+                for k, v in class_flops(R, c).items():
                     fl[k] = fl.get(k, 0.0) + v
         else:
-            fl = flops_breakdown(R, C)
+            fl = class_flops(R, C)
         if shard:                                       # per-rank share of the one sharded MSA
             fl = {k: v / world for k, v in fl.items()}
         gemm_classes = ["linear_qkv", "linear_out_resid", "linear_fc1_gelu", "linear_fc2_resid"]

@@ -135,6 +135,19 @@ int rnamsm_linear_residual_layernorm(const void* x, const void* W, const float* 
                                      float* resid, const float* ln_w, const float* ln_b, float eps, void* y, int y_dtype,
                                      int tr_R, int tr_C, int* counters, void* stream);
 
+/* K4 + K5 + K6 in ONE launch for short alignments (C <= 128), 16-bit dtypes only: tied logits per (head, row chunk) ->
+ * grid barrier -> softmax with key mask (fp32 map into probs_out [H,C,C], 16-bit rows into probs_lp [H,C,ld_lp]) ->
+ * grid barrier -> ctx [R*C, H*64] = P V (modules.py:752-821).  A cooperative launch of H x n_chunks CTAs; this is the
+ * route rnamsm_layer_forward / rnamsm_msa_forward / rnamsm_msa_forward_batch take whenever
+ * rnamsm_row_attn_short_chunks(R, C, H) > 0 (it returns 0 for C > 128 or with RNAMSM_ROW_SHORT=0 in the environment).
+ * partial: fp32 scratch [n_chunks, H, C, C]; n_chunks as returned by rnamsm_row_attn_short_chunks (any value with
+ * H * n_chunks <= #SMs and no empty chunk is accepted).  Split sums are taken in a fixed order: results do not
+ * depend on timing. */
+int rnamsm_row_attn_short_chunks(int R, int C, int H);
+int rnamsm_row_attn_short(const void* qkv, int R, int C, int H, int dtype, const uint8_t* key_pad, float logit_scale,
+                          float* partial, int n_chunks, float* probs_out, void* probs_lp, int ld_lp, void* ctx,
+                          void* stream);
+
 /* Suggested split count for K4: as many row ranges as fit ONE wave of the launch (74 CTA pairs in the
  * 16-bit path), at least 8 rows each. */
 int rnamsm_row_attn_splits(int R, int C, int H, int dtype);

@@ -58,6 +58,8 @@ SIGNATURES = {
     "rnamsm_linear_residual_layernorm": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp]),
     "rnamsm_row_attn_logits": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "rnamsm_row_attn_splits": (_i, [_i, _i, _i, _i]),
+    "rnamsm_row_attn_short_chunks": (_i, [_i, _i, _i]),
+    "rnamsm_row_attn_short": (_i, [_vp, _i, _i, _i, _i, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "rnamsm_row_softmax": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _i, _i, _vp]),
     "rnamsm_row_attn_av": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "rnamsm_col_attn": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

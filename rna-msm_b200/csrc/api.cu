@@ -37,7 +37,7 @@ static std::vector<ProfEvent> g_prof_events;
 static std::vector<cudaEvent_t> g_prof_pool;
 static const char* kClassNames[KC_COUNT] = {"embed_ln", "layernorm", "row_softmax", "vocab_proj", "linear_qkv",
                                             "linear_fc1_gelu", "linear_out_resid", "linear_fc2_resid",
-                                            "row_logits", "row_av", "col_attn", "contact_head"};
+                                            "row_logits", "row_av", "col_attn", "contact_head", "row_attn_short"};
 static cudaEvent_t prof_get_event() {
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
   cudaEvent_t e = nullptr;
@@ -132,6 +132,7 @@ static size_t tf32_scratch_bytes(long long M, int N, int K);
 struct Plan {
   size_t el;  // bytes per element of the compute dtype
   int splits, ldp;
+  int short_chunks;   // > 0: the tied row attention runs as ONE launch (row_attn_short.cu) with this many row chunks = splits
   size_t off_xn, off_qkvh, off_partial, off_probs, off_map, off_cnt, off_split, total;
 };
 
@@ -152,7 +153,8 @@ static Plan make_plan(int R, int C, int D, int H, int F, int dtype, bool f32_ten
   Plan p{};
   const size_t T = (size_t)R * C;
   p.el = is16(dtype) ? 2 : 4;
-  p.splits = pick_splits(R, C, H, dtype);
+  p.short_chunks = is16(dtype) ? row_attn_short_chunks(R, C, H) : 0;
+  p.splits = p.short_chunks > 0 ? p.short_chunks : pick_splits(R, C, H, dtype);
   p.ldp = is16(dtype) ? (C + 7) / 8 * 8 : C;
   size_t o = 0;
   p.off_xn = o;      o += align256(T * D * p.el);
@@ -267,17 +269,24 @@ static int layer_forward(const rnamsm_layer_weights* w, int D, int H, int F, flo
     if ((rc = linear_any(xn, w->row.w_qkv, T, 3 * D, D, row_dt, e, qkv, st, nullptr, split))) return rc;
     if ((rc = range_watch(xn, T * D, row_dt, st)) || (rc = range_watch(qkv, T * 3 * D, row_dt, st))) return rc;
   }
-  if (is16(row_dt)) {
-    if ((rc = launch_row_logits_16(qkv, R, C, H, row_dt == RNAMSM_F16, partial, p.splits, st))) return rc;
-  } else {
-    if ((rc = launch_row_logits_f32((const float*)qkv, R, C, H, partial, p.splits, st))) return rc;
-  }
   // key mask comes from MSA row 0 (padding_mask[:, 0], modules.py:780-784) = first C entries of pad
-  if ((rc = launch_row_softmax(partial, p.splits, H, C, pad, logit_scale, map, probs_lp, p.ldp, row_dt, st))) return rc;
-  if (is16(row_dt)) {
-    if ((rc = launch_row_av_16(probs_lp, p.ldp, qkv, R, C, H, row_dt == RNAMSM_F16, ctx, st))) return rc;
+  if (is16(row_dt) && p.short_chunks > 0) {
+    // short alignment (C <= 128): logits -> softmax -> A V in one cooperative launch (row_attn_short.cu)
+    if ((rc = launch_row_attn_short_16(qkv, R, C, H, row_dt == RNAMSM_F16, partial, p.short_chunks, pad, logit_scale, map,
+                                       probs_lp, p.ldp, ctx, st)))
+      return rc;
   } else {
-    if ((rc = launch_row_av_f32(map, C, (const float*)qkv, R, C, H, (float*)ctx, st))) return rc;
+    if (is16(row_dt)) {
+      if ((rc = launch_row_logits_16(qkv, R, C, H, row_dt == RNAMSM_F16, partial, p.splits, st))) return rc;
+    } else {
+      if ((rc = launch_row_logits_f32((const float*)qkv, R, C, H, partial, p.splits, st))) return rc;
+    }
+    if ((rc = launch_row_softmax(partial, p.splits, H, C, pad, logit_scale, map, probs_lp, p.ldp, row_dt, st))) return rc;
+    if (is16(row_dt)) {
+      if ((rc = launch_row_av_16(probs_lp, p.ldp, qkv, R, C, H, row_dt == RNAMSM_F16, ctx, st))) return rc;
+    } else {
+      if ((rc = launch_row_av_f32(map, C, (const float*)qkv, R, C, H, (float*)ctx, st))) return rc;
+    }
   }
   // ---- column attention over the MSA depth                           modules.py:875-945
   // 16-bit path: LayerNorm writes its output in column-major token order (c * R + r), so the QKV GEMM
@@ -418,13 +427,19 @@ static int layer_forward_batch(const rnamsm_layer_weights* w, int D, int H, int 
     float* map = (row_attn_out && row_attn_out[i])
                      ? row_attn_out[i] + (size_t)layer * H * C[i] * C[i]
                      : reinterpret_cast<float*>(ws + bp.off_map);
-    if ((rc = launch_row_logits_16(qkv_i, R[i], C[i], H, row_dt == RNAMSM_F16, partial, p.splits, st))) return rc;
-    if ((rc = launch_row_softmax(partial, p.splits, H, C[i], pad_i, 1.0f / sqrtf((float)R[i]), map, probs_lp, p.ldp,
-                                 row_dt, st)))
-      return rc;
-    if ((rc = launch_row_av_16(probs_lp, p.ldp, qkv_i, R[i], C[i], H, row_dt == RNAMSM_F16, ctx + (size_t)off * D * el,
-                               st)))
-      return rc;
+    if (p.short_chunks > 0) {   // the same one-launch kernel rnamsm_msa_forward uses for this shape (bit-identical results)
+      if ((rc = launch_row_attn_short_16(qkv_i, R[i], C[i], H, row_dt == RNAMSM_F16, partial, p.short_chunks, pad_i,
+                                         1.0f / sqrtf((float)R[i]), map, probs_lp, p.ldp, ctx + (size_t)off * D * el, st)))
+        return rc;
+    } else {
+      if ((rc = launch_row_logits_16(qkv_i, R[i], C[i], H, row_dt == RNAMSM_F16, partial, p.splits, st))) return rc;
+      if ((rc = launch_row_softmax(partial, p.splits, H, C[i], pad_i, 1.0f / sqrtf((float)R[i]), map, probs_lp, p.ldp,
+                                   row_dt, st)))
+        return rc;
+      if ((rc = launch_row_av_16(probs_lp, p.ldp, qkv_i, R[i], C[i], H, row_dt == RNAMSM_F16, ctx + (size_t)off * D * el,
+                                 st)))
+        return rc;
+    }
     off += (long long)R[i] * C[i];
   }
   {
@@ -569,6 +584,16 @@ int rnamsm_row_attn_splits(int R, int C, int H, int dtype) { return pick_splits(
 int rnamsm_row_attn_logits(const void* qkv, int R, int C, int H, int dtype, float* partial, int n_splits, void* stream) {
   if (is16(dtype)) return launch_row_logits_16(qkv, R, C, H, dtype == RNAMSM_F16, partial, n_splits, (cudaStream_t)stream);
   return launch_row_logits_f32((const float*)qkv, R, C, H, partial, n_splits, (cudaStream_t)stream);
+}
+
+int rnamsm_row_attn_short_chunks(int R, int C, int H) { return row_attn_short_chunks(R, C, H); }
+
+int rnamsm_row_attn_short(const void* qkv, int R, int C, int H, int dtype, const uint8_t* key_pad, float logit_scale,
+                          float* partial, int n_chunks, float* probs_out, void* probs_lp, int ld_lp, void* ctx,
+                          void* stream) {
+  RNAMSM_REQUIRE(is16(dtype), "rnamsm_row_attn_short: 16-bit dtypes only (the fp32 path keeps the three-kernel chain)");
+  return launch_row_attn_short_16(qkv, R, C, H, dtype == RNAMSM_F16, partial, n_chunks, key_pad, logit_scale, probs_out,
+                                  probs_lp, ld_lp, ctx, (cudaStream_t)stream);
 }
 
 int rnamsm_row_softmax(const float* partial, int n_splits, int H, int C, const uint8_t* key_pad, float logit_scale,

@@ -14,7 +14,7 @@ long long launch_count();
 // for the live roofline figure and the per-kernel time shares.  Off by default: zero overhead.
 enum KernelClass {
   KC_EMBED_LN = 0, KC_LAYERNORM, KC_ROW_SOFTMAX, KC_VOCAB_PROJ, KC_LINEAR_QKV, KC_LINEAR_FC1, KC_LINEAR_OUT,
-  KC_LINEAR_FC2, KC_ROW_LOGITS, KC_ROW_AV, KC_COL_ATTN, KC_CONTACT, KC_COUNT
+  KC_LINEAR_FC2, KC_ROW_LOGITS, KC_ROW_AV, KC_COL_ATTN, KC_CONTACT, KC_ROW_SHORT, KC_COUNT
 };
 struct ProfScope {
   int cls;
@@ -92,6 +92,13 @@ int launch_linear_16_scatter(const void* x, const void* W, const float* bias, in
                              void* const* peer_x, int n_ranks, int Rn, int C, int c0, int as_delta16, cudaStream_t st);
 int launch_add_layernorm(float* x, const void* delta, int delta_dtype, const float* w, const float* b, void* y,
                          int y_dtype, long long n_rows, int D, float eps, cudaStream_t st);
+
+// row_attn_short.cu -- the whole tied row attention of a short alignment (C <= 128) in one cooperative launch:
+// partial logits per (head, row chunk) -> grid barrier -> softmax (fp32 map + 16-bit P) -> grid barrier -> P V.
+// row_attn_short_chunks: the chunk (= split) count that path uses for a shape, 0 when it does not apply.
+int row_attn_short_chunks(int R, int C, int H);
+int launch_row_attn_short_16(const void* qkv, int R, int C, int H, int fp16, float* partial, int n_chunks, const uint8_t* key_pad,
+                             float logit_scale, float* map, void* probs_lp, int ldp, void* ctx, cudaStream_t st);
 
 // col_attn_umma.cu
 int launch_col_attn_16(const void* qkv, int R, int C, int H, int fp16, int col_major, const uint8_t* pad, void* ctx,

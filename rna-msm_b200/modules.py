@@ -150,20 +150,28 @@ class RowSelfAttention(_AxialAttentionBase):
                 xb = x[:, :, b, :].to(dt).contiguous().view(R * Cc, D)
                 pad = _pad_u8(self_attn_padding_mask, b)
                 qkv = _linear(xb, w_qkv, b_qkv, code, L.EPI_BIAS, q_scale, D, pad)
-                splits = L.lib.rnamsm_row_attn_splits(R, Cc, H, code)
-                partial = torch.empty((splits, H, Cc, Cc), dtype=torch.float32, device=x.device)
-                L.check(L.lib.rnamsm_row_attn_logits(L.ptr(qkv), R, Cc, H, code, L.ptr(partial), splits, st), "row_attn_logits")
                 pmap = torch.empty((H, Cc, Cc), dtype=torch.float32, device=x.device)
+                ctx = torch.empty((R * Cc, D), dtype=dt, device=x.device)
                 if code != L.F32:
                     ldp = (Cc + 7) // 8 * 8
                     plp = torch.empty((H, Cc, ldp), dtype=dt, device=x.device)
                 else:
                     ldp, plp = Cc, None
-                L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), splits, H, Cc, L.ptr(pad), float(logit_scale),
-                                                 L.ptr(pmap), L.ptr(plp), ldp, code, st), "row_softmax")
-                ctx = torch.empty((R * Cc, D), dtype=dt, device=x.device)
-                L.check(L.lib.rnamsm_row_attn_av(L.ptr(plp if plp is not None else pmap), ldp, L.ptr(qkv), R, Cc, H,
-                                                 code, L.ptr(ctx), st), "row_attn_av")
+                chunks = L.lib.rnamsm_row_attn_short_chunks(R, Cc, H) if code != L.F32 else 0
+                if chunks > 0:
+                    # short alignment (C <= 128): K4 + K5 + K6 in one cooperative launch, as the fused layer does
+                    partial = torch.empty((chunks, H, Cc, Cc), dtype=torch.float32, device=x.device)
+                    L.check(L.lib.rnamsm_row_attn_short(L.ptr(qkv), R, Cc, H, code, L.ptr(pad), float(logit_scale),
+                                                        L.ptr(partial), chunks, L.ptr(pmap), L.ptr(plp), ldp, L.ptr(ctx), st),
+                            "row_attn_short")
+                else:
+                    splits = L.lib.rnamsm_row_attn_splits(R, Cc, H, code)
+                    partial = torch.empty((splits, H, Cc, Cc), dtype=torch.float32, device=x.device)
+                    L.check(L.lib.rnamsm_row_attn_logits(L.ptr(qkv), R, Cc, H, code, L.ptr(partial), splits, st), "row_attn_logits")
+                    L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), splits, H, Cc, L.ptr(pad), float(logit_scale),
+                                                     L.ptr(pmap), L.ptr(plp), ldp, code, st), "row_softmax")
+                    L.check(L.lib.rnamsm_row_attn_av(L.ptr(plp if plp is not None else pmap), ldp, L.ptr(qkv), R, Cc, H,
+                                                     code, L.ptr(ctx), st), "row_attn_av")
                 ob = _linear(ctx, w_out, b_out, code)
                 out[:, :, b, :] = ob.view(R, Cc, D).float()
                 probs[:, b] = pmap

@@ -257,6 +257,57 @@ def test_row_attention_chain(L, R, C, code):
     assert rel(ctx, ctx_ref) < tol(code)
 
 
+@pytest.mark.parametrize("R,C,with_pad", [(2, 5, False), (7, 36, True), (33, 16, False), (64, 48, True), (130, 64, True),
+                                          (512, 36, False), (100, 65, True), (61, 100, False), (300, 128, True),
+                                          (1, 20, False), (515, 127, True)])
+@pytest.mark.parametrize("code", [1, 2], ids=["bf16", "f16"])
+def test_row_attention_short(L, R, C, with_pad, code):
+    """K4 + K5 + K6 in one cooperative launch (C <= 128) against float64, and against the three-kernel chain."""
+    qkv, q64 = make_qkv(R, C, 23, code, L, 0.4)
+    q = q64[..., :D].view(R, C, H, 64)
+    k = q64[..., D:2 * D].view(R, C, H, 64)
+    v = q64[..., 2 * D:].view(R, C, H, 64)
+    logits_ref = torch.einsum("rihd,rjhd->hij", q, k)
+    key_pad = torch.zeros(C, dtype=torch.uint8)
+    if with_pad:
+        key_pad[-2:] = 1
+    logit_scale = 1.0 / math.sqrt(R)
+    masked = (logits_ref * logit_scale).float().masked_fill(key_pad.bool()[None, None, :], -10000)
+    probs_ref = masked.double().softmax(-1)
+    chunks = L.lib.rnamsm_row_attn_short_chunks(R, C, H)
+    assert 1 <= chunks <= R and chunks * H <= 148
+    ldp = (C + 7) // 8 * 8
+    key_pad_dev = key_pad.cuda() if with_pad else None
+    dt = L.torch_dtype(code)
+    for n_chunks in sorted({chunks, 1, min(R, 5)}):
+        if (n_chunks - 1) * math.ceil(R / n_chunks) >= R:
+            continue
+        partial = torch.full((n_chunks, H, C, C), float("nan"), device="cuda")
+        pmap = torch.full((H, C, C), float("nan"), device="cuda")
+        plp = torch.full((H, C, ldp), 7.0, dtype=dt, device="cuda")
+        ctx = torch.full((R * C, D), float("nan"), dtype=dt, device="cuda")
+        for _ in range(2):                              # twice: the barrier counter must come back to zero
+            L.check(L.lib.rnamsm_row_attn_short(L.ptr(qkv), R, C, H, code, L.ptr(key_pad_dev), logit_scale, L.ptr(partial),
+                                                n_chunks, L.ptr(pmap), L.ptr(plp), ldp, L.ptr(ctx), L.stream_ptr()))
+        torch.cuda.synchronize()
+        # (one chunk = one tensor-core accumulator over all R x 64 products: its truncating fp32 adds reach 3e-5 at R = 512)
+        assert rel(partial.sum(0), logits_ref) < (2e-5 if R // n_chunks <= 128 else 6e-5), f"chunks={n_chunks}"
+        assert rel(pmap, probs_ref) < (2e-5 if R // n_chunks <= 128 else 1e-4)
+        assert rel(plp[..., :C], probs_ref) < 5e-3
+        assert float(plp[..., C:].float().abs().sum()) == 0.0
+        ctx_ref = torch.einsum("hij,rjhd->rihd", plp[..., :C].double().cpu(), v).reshape(R * C, D)
+        assert rel(ctx, ctx_ref) < tol(code)
+    # the three-kernel chain on the same partial sums agrees to fp32 rounding (its softmax is compiled separately)
+    pmap2 = torch.empty(H, C, C, device="cuda")
+    plp2 = torch.empty(H, C, ldp, dtype=dt, device="cuda")
+    L.check(L.lib.rnamsm_row_softmax(L.ptr(partial), n_chunks, H, C, L.ptr(key_pad_dev), logit_scale, L.ptr(pmap2),
+                                     L.ptr(plp2), ldp, code, L.stream_ptr()))
+    assert rel(pmap, pmap2) < 1e-6 and rel(plp, plp2) < 5e-3
+    ctx2 = torch.empty(R * C, D, dtype=dt, device="cuda")
+    L.check(L.lib.rnamsm_row_attn_av(L.ptr(plp2), ldp, L.ptr(qkv), R, C, H, code, L.ptr(ctx2), L.stream_ptr()))
+    assert rel(ctx, ctx2.double().cpu()) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------ K7
 @pytest.mark.parametrize("R,C,with_pad", [(2, 5, False), (9, 7, True), (64, 3, False), (65, 4, True), (130, 6, True),
                                           (300, 2, False), (257, 3, True), (300, 7, True), (520, 13, False),
