@@ -62,7 +62,16 @@ struct ShortArgs {
   const uint8_t* key_pad;     // [C] or nullptr (MSA row 0 of the padding mask, modules.py:780-784)
   float logit_scale;          // 1 / sqrt(R) (q carries 64^-1/2)
   unsigned* sync;             // grid barrier counter, zero between launches
+  long long* trace;           // debug (RNAMSM_SHORT_TRACE=1): globaltimer of CTA 0 / thread 0 at the phase boundaries
 };
+
+__device__ __forceinline__ void trace_mark(const ShortArgs& a, int slot) {
+  if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.trace[slot] = t;
+  }
+}
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -94,6 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 row_attn_short_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_p,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const ShortArgs a) {
   extern __shared__ uint8_t smem_raw[];
+  trace_mark(a, 0);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* full1 = bars;                       // [kMaxStages] phase 1 ring
@@ -145,6 +155,7 @@ row_attn_short_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  trace_mark(a, 1);
 
   // =========================== phase 1: partial logits of (head h, rows r0..r1) ===========================
   if (warp == 0 && lane == 0) {
@@ -161,6 +172,7 @@ row_attn_short_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_co
     // V does not depend on P: once this CTA's last logit MMA has read the ring, the first P V groups are fetched
     // behind the two grid barriers and the softmax
     mbar_wait(s_done, 0);
+    trace_mark(a, 2);
     for (int g = 0; g < min(n_grp3, ns3); ++g) {
       mbar_expect_tx(&full3[g], stg3);
       tma_load_3d(smem + OFF_RING + g * stg3, &tm_v, &full3[g], 2 * D + h * 64, 0, r0 + g * GV);   // v: [GV][CP][64]
@@ -207,7 +219,9 @@ row_attn_short_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_co
     }
     tc_fence_before();
   }
+  trace_mark(a, 3);
   grid_barrier(a.sync, gridDim.x);
+  trace_mark(a, 4);
 
   // =========================== phase 2: softmax rows i = chunk, chunk + n_chunks, ... of head h ===========
   {
@@ -254,7 +268,9 @@ row_attn_short_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_co
       }
     }
   }
+  trace_mark(a, 5);
   grid_barrier(a.sync, 2 * gridDim.x);
+  trace_mark(a, 6);
 
   // =========================== phase 3: ctx rows r0..r1 of head h = P V ===================================
   if (warp == 0 && lane == 0) {
@@ -334,8 +350,10 @@ row_attn_short_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_co
     if (lane == 0) bulk_wait_all0();
   }
 
+  if (warp == 0 && lane == 0) trace_mark(a, 7);     // producer done issuing
   tc_fence_before();
   __syncthreads();
+  trace_mark(a, 8);
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
   // the counter goes back to zero for the next launch: every CTA passed the second barrier before its third arrival
   if (threadIdx.x == 0 && atomicAdd(a.sync, 1u) == 3u * gridDim.x - 1u) atomicExch(a.sync, 0u);
@@ -368,11 +386,29 @@ int launch_short(const CUtensorMap& tqk, const CUtensorMap& tp, const CUtensorMa
     RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(row_attn_short_kernel<kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
-  void* params[] = {(void*)&tqk, (void*)&tp, (void*)&tv, (void*)&to, (void*)&a};
-  ProfScope prof(KC_ROW_SHORT, st);
-  RNAMSM_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)row_attn_short_kernel<kFp16>, dim3(a.H * a.n_chunks), dim3(kThreads),
-                                                params, (size_t)kSmem, st));
+  static int want_trace = -1;
+  if (want_trace < 0) want_trace = getenv("RNAMSM_SHORT_TRACE") ? 1 : 0;
+  ShortArgs args = a;
+  if (want_trace) {
+    static long long* dbuf = nullptr;
+    if (!dbuf) { cudaMalloc(&dbuf, 16 * sizeof(long long)); }
+    args.trace = dbuf;
+  }
+  void* params[] = {(void*)&tqk, (void*)&tp, (void*)&tv, (void*)&to, (void*)&args};
+  {
+    ProfScope prof(KC_ROW_SHORT, st);
+    RNAMSM_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)row_attn_short_kernel<kFp16>, dim3(a.H * a.n_chunks),
+                                                  dim3(kThreads), params, (size_t)kSmem, st));
+  }
   count_launch();
+  if (want_trace) {       // debug: phase boundaries of CTA 0 in ns since its first instruction
+    long long h[16];
+    RNAMSM_CHECK_CUDA(cudaStreamSynchronize(st));
+    RNAMSM_CHECK_CUDA(cudaMemcpy(h, args.trace, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "row_attn_short R=%d C=%d: prologue %lld | logits %lld | epi1 %lld | barrier1 %lld | softmax %lld | barrier2 %lld | "
+            "PV issue %lld | drain %lld | total %lld ns\n", a.R, a.C, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4],
+            h[6] - h[5], h[7] - h[6], h[8] - h[7], h[8] - h[0]);
+  }
   return 0;
 }
 
