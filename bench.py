@@ -396,6 +396,40 @@ def run_secondary(args, pkg, _lib, world, rank, peaks):
         del tok_dev, atp_host, emb_host
         return res
 
+    def farm_cfg3(model):
+        """BASELINE configs[2]: the batch of 64 MSAs (depth 256, L 50-500), LPT-assigned to the ranks, no collective on
+        the data path.  One pass = every rank runs its MSAs; time = max over ranks; tokens/s = whole batch / time."""
+        Rf = WORKLOADS["cfg3"][0]
+        lens = cfg3_lengths()
+        mine = lpt_assign([total_flops(Rf, c) for c in lens], world)[rank]
+        toks = [synthetic_tokens(Rf, lens[i], seed=200 + i).cuda() for i in mine]
+        bt = 131072
+        groups = pkg.plan_batches([(Rf, lens[i]) for i in mine], bt)
+
+        def one_by_one():
+            for t in toks:
+                model(t, repr_layers=[NL], need_head_weights=True, want_logits=False)
+
+        def batched():
+            for g in groups:
+                model.forward_batch([toks[i] for i in g], need_head_weights=True)
+
+        res = {"workload": WORKLOADS["cfg3"][3], "n_msa": len(lens), "R": Rf, "n_gpus": world,
+               "tokens_per_pass": Rf * sum(lens), "parallelism": f"dp{world} independent MSAs (LPT by flops), no collective"}
+        for key, fn in (("one_forward_per_msa", one_by_one), ("forward_batch", batched)):
+            sync_all()
+            ms = time_events(fn, 2, 1)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t[0])
+            res[key] = {"ms_per_pass": round(ms, 3), "tokens_per_s": round(Rf * sum(lens) / (ms * 1e-3), 1)}
+        res["forward_batch"]["batch_tokens"] = bt
+        res["forward_batch"]["passes_on_rank0"] = len(groups)
+        del toks
+        torch.cuda.empty_cache()
+        return res
+
     big = (("cfg5", 1024, 1024, True), ("cfg4", 4096, 128, False))
     if world == 1:
         models = {}
@@ -405,6 +439,10 @@ def run_secondary(args, pkg, _lib, world, rank, peaks):
             out[name] = {"workload": WORKLOADS[name][3], "R": R, "C": C,
                          **single_gpu(models[epm], R, C, steps if name != "cfg1" else 10, True)}
             torch.cuda.empty_cache()
+        try:
+            out["cfg3"] = farm_cfg3(models[True])
+        except Exception as e:                          # never lose the main line to a secondary measurement
+            out["cfg3"] = {"error": repr(e)[:300]}
         models.clear()
         torch.cuda.empty_cache()
         for key, prec, what in (("cfg2_fp32", "fp32", "fp32 path (FFMA, the <= 1e-4 parity path)"),
@@ -481,6 +519,13 @@ def run_secondary(args, pkg, _lib, world, rank, peaks):
         except Exception as e:
             entry["error"] = repr(e)[:300]
         out[name] = entry
+    try:
+        if True not in models:
+            models[True] = make_model(True)
+        res3 = farm_cfg3(models[True])
+        out["cfg3"] = res3
+    except Exception as e:
+        out["cfg3"] = {"error": repr(e)[:300]}
     # ---- multi-rank parity: the sharded forward against the one-GPU forward of the same model, small padded MSA ----
     try:
         Rp, Cp = 64, 128
