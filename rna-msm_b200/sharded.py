@@ -60,6 +60,24 @@ class ShardPlan:
         return {"all_to_all_fwd": a2a, "all_to_all_back": a2a, "logit_all_reduce": ar}
 
 
+def pad_to_shards(tokens: torch.Tensor, world: int, col_multiple: int, pad_idx: int) -> torch.Tensor:
+    """``[1, R, C]`` tokens padded with ``<pad>`` rows / columns so that ``world`` divides the depth and
+    ``world * col_multiple`` the width (uneven shards).  Result-neutral for the real tokens PROVIDED the caller
+    keeps the TRUE depth in ``align_scaling`` (``1/sqrt(R)``, modules.py:713-715) -- which both schedules below do: a pad
+    row has ``q = 0`` (modules.py:767-772: no contribution to the tied logits) and is a masked key of the column attention
+    (modules.py:911-915, ``exp(-10000 - max)`` is exactly 0 in fp32); a pad column is a masked key of the row attention
+    (modules.py:780-784) and an independent, discarded item of the column attention."""
+    _, R, C = tokens.shape
+    Rp = -(-R // world) * world
+    cm = world * max(1, col_multiple)
+    Cp = -(-C // cm) * cm
+    if Rp == R and Cp == C:
+        return tokens
+    out = torch.full((1, Rp, Cp), pad_idx, dtype=tokens.dtype, device=tokens.device)
+    out[:, :R, :C] = tokens
+    return out
+
+
 class ShardedMSAForward:
     """MSATransformer.forward (model.py:338-416) for ONE MSA sharded over a process group.
 
@@ -93,6 +111,8 @@ class ShardedMSAForward:
     def forward(self, tokens: torch.Tensor, need_head_weights: bool = True, gather_rows: bool = False,
                 pad_idx: int = 1) -> Dict[str, object]:
         assert tokens.ndim == 3 and tokens.shape[0] == 1, "one MSA per call: tokens [1, R, C]"
+        _, Rt, Ct = tokens.shape                                                    # the TRUE shape: scaling, outputs
+        tokens = pad_to_shards(tokens, self.world, 1, pad_idx)
         _, R, C = tokens.shape
         plan = ShardPlan(R, C, self.world, self.rank)
         n, Rn, Cn = plan.world, plan.Rn, plan.Cn
@@ -104,14 +124,14 @@ class ShardedMSAForward:
         pad_cols = pad_full[:, plan.cols()].contiguous() if has_pad else None       # [R, Cn] this rank's columns
         key_pad = pad_full[0].contiguous() if has_pad else None                     # MSA row 0, modules.py:780-784
 
-        x = ops.embed(tok[plan.rows()].contiguous(), plan.r0, R)                    # [Rn*C, D] fp32
+        x = ops.embed(tok[plan.rows()].contiguous(), plan.r0, Rt)                   # [Rn*C, D] fp32
         D = x.shape[-1]
         maps = ops.new_maps(N, C) if need_head_weights else None
         for l in range(N):
             # ---- tied row attention on the row shard ----------------------------------------------
-            partial = ops.row_logits(l, x, Rn, C, pad_rows, R)                      # [S, H, C, C] fp32, local rows
+            partial = ops.row_logits(l, x, Rn, C, pad_rows, Rt)                     # [S, H, C, C] fp32, local rows
             partial = self._sum_over_ranks(partial)                                 # <-- fused P2P site 1
-            ops.row_finish(l, x, partial, Rn, C, key_pad, R, None if maps is None else maps[l])
+            ops.row_finish(l, x, partial, Rn, C, key_pad, Rt, None if maps is None else maps[l])
             # ---- column attention on the column shard ---------------------------------------------
             xn = ops.col_prepare(l, x, Rn, C)                                       # [Rn*C, D] 16-bit (fp32 path: fp32)
             send = xn.view(Rn, n, Cn, D).permute(1, 0, 2, 3).contiguous()           # [n(dest), Rn, Cn, D]
@@ -123,13 +143,18 @@ class ShardedMSAForward:
             ops.ffn(l, x, Rn * C)
         ops.final_ln(x, Rn * C)
         rep = x.view(1, Rn, C, D)
+        valid = max(0, min(Rn, Rt - plan.r0))                                       # real rows of this shard
         if gather_rows and n > 1:
             full = [torch.empty_like(rep) for _ in range(n)]
             dist.all_gather(full, rep.contiguous(), group=self.group)
-            rep = torch.cat(full, 1)
-        out: Dict[str, object] = {"logits": None, "representations": {N: rep}, "row_shard": (plan.r0, plan.r0 + Rn)}
+            rep = torch.cat(full, 1)[:, :Rt, :Ct]
+        elif (R, C) != (Rt, Ct):
+            rep = rep[:, :valid, :Ct].contiguous()
+        out: Dict[str, object] = {"logits": None, "representations": {N: rep}, "row_shard": (plan.r0, plan.r0 + valid)}
         if maps is not None:
             out["row_attentions"] = maps.view(1, N, maps.shape[1], C, C)
+            if C != Ct:
+                out["row_attentions"] = out["row_attentions"][..., :Ct, :Ct].contiguous()
         return out
 
 
@@ -170,7 +195,10 @@ class CudaShardOps:
         x = torch.empty((Rn * C, self.D), dtype=torch.float32, device=self.dev)
         row_pos = None
         if m.msa_position_embedding is not None:
-            row_pos = m.msa_position_embedding.detach().reshape(-1)[r0:r0 + Rn].float().contiguous()
+            table = m.msa_position_embedding.detach().reshape(-1).float()
+            row_pos = torch.zeros(Rn, dtype=torch.float32, device=self.dev)           # rows past the table: <pad> rows only
+            have = max(0, min(Rn, table.numel() - r0))
+            row_pos[:have] = table[r0:r0 + have]
         self._keep = row_pos
         toks = tokens_rows.long().contiguous()
         L.check(L.lib.rnamsm_embed_layernorm(
@@ -504,6 +532,8 @@ class FusedShardedForward:
                 gather_maps: bool = True) -> Dict[str, object]:
         L, m, ops = self.L, self.m, self.ops
         assert tokens.ndim == 3 and tokens.shape[0] == 1, "one MSA per call: tokens [1, R, C]"
+        _, Rt, Ct = tokens.shape                                                    # the TRUE shape: scaling, outputs
+        tokens = pad_to_shards(tokens, self.world, 16, pad_idx)                     # (16: TMA box rows of the scatter GEMM)
         _, R, C = tokens.shape
         plan = ShardPlan(R, C, self.world, self.rank)
         n, Rn, Cn, g = plan.world, plan.Rn, plan.Cn, plan.rank
@@ -539,9 +569,9 @@ class FusedShardedForward:
         pad_cols = CudaShardOps._u8(pad_full[:, plan.cols()]) if has_pad else None
         key_pad = CudaShardOps._u8(pad_full[0]) if has_pad else None
 
-        x.copy_(ops.embed(tok[plan.rows()].contiguous(), plan.r0, R))
+        x.copy_(ops.embed(tok[plan.rows()].contiguous(), plan.r0, Rt))
         self._barrier()                                   # every rank's buffers are initialised / the previous call is over
-        logit_scale = 1.0 / math.sqrt(R)
+        logit_scale = 1.0 / math.sqrt(Rt)                 # align_scaling with the true depth (pad rows add nothing)
         for l in range(N):
             layer = m.layers[l]
             # ---- tied row attention ------------------------------------------------------------------
@@ -598,10 +628,13 @@ class FusedShardedForward:
             hdn = self._linear(xn_f, w1, b1, code, L.EPI_BIAS_GELU)
             self._linear(hdn, w2, b2, code, L.EPI_BIAS_RESIDUAL, out=x)
         ops.final_ln(x, Rn * C)
-        rep = x.view(1, Rn, C, D).clone()                 # a fresh tensor: the peer buffer is rewritten by the next call
-        out: Dict[str, object] = {"logits": None, "representations": {N: rep}, "row_shard": (plan.r0, plan.r0 + Rn)}
+        valid = max(0, min(Rn, Rt - plan.r0))             # real rows of this shard
+        rep = x.view(1, Rn, C, D)[:, :valid, :Ct].clone()  # a fresh tensor: the peer buffer is rewritten by the next call
+        out: Dict[str, object] = {"logits": None, "representations": {N: rep}, "row_shard": (plan.r0, plan.r0 + valid)}
         if host_out is not None:
             if g == 0:                                    # rank 0 owns MSA row 0 = the source of *_emb.npy
+                if host_out.start + host_out.Ls > Ct:
+                    raise ValueError(f"host_out was built for C={host_out.C}, tokens have C={Ct}")
                 host_out.emb.copy_(rep[0, 0, host_out.start:host_out.start + host_out.Ls], non_blocking=True)
             with torch.cuda.stream(side):                 # returns once EVERY rank's rows have landed in host memory
                 self._barrier(1, side.cuda_stream)
@@ -617,9 +650,12 @@ class FusedShardedForward:
                     out["row_attentions"] = torch.cat(parts, 2).view(1, N, H, C, C)
                 else:
                     out["row_attentions"] = maps.view(1, N, H, C, C)
+                if C != Ct:
+                    out["row_attentions"] = out["row_attentions"][..., :Ct, :Ct].contiguous()
             else:
-                out["row_attentions_rows"] = rows
-                out["row_attentions_range"] = (i0, i1)
+                hi = max(i0, min(i1, Ct))                 # real query rows this rank owns
+                out["row_attentions_rows"] = rows[:, :, :hi - i0, :Ct] if C != Ct else rows
+                out["row_attentions_range"] = (i0, hi)
         return out
 
 

@@ -79,7 +79,37 @@ def test_world1_fused_matches_model_forward(pads, scatter_fp32, monkeypatch):
     assert torch.equal(keep_rep, out["representations"][3])
 
 
-def _worker(rank, world, port, precision, q):
+@pytest.mark.parametrize("fused", [False, True], ids=["nccl", "fused"])
+def test_world1_uneven_shape_is_padded_inside(fused):
+    """Shapes the shard plan cannot split (here: C not a multiple of the fused schedule's 16-column boxes) are padded
+    with <pad> inside the sharded forward and come back in the caller's shape, equal to the plain forward on every real
+    token (align_scaling keeps the TRUE depth)."""
+    import rnamsm_b200 as pkg
+    from rnamsm_b200 import sharded
+    from rnamsm_b200.sharded import ShardedHostOutput, pad_to_shards, sharded_forward
+    sharded._FUSED_CACHE.clear()
+    m = _model(pkg, 3, "fp16", "cuda")
+    tokens = O.make_tokens(37, 71, 4).cuda()
+    assert tuple(pad_to_shards(tokens, 1, 16, 1).shape) == (1, 37, 80) and pad_to_shards(tokens, 1, 1, 1) is tokens
+    assert tuple(pad_to_shards(tokens, 8, 16, 1).shape) == (1, 40, 128)
+    ref = m(tokens, repr_layers=[3], need_head_weights=True, want_logits=False)
+    out = sharded_forward(m, tokens, fused=fused)
+    torch.cuda.synchronize()
+    assert tuple(out["representations"][3].shape) == (1, 37, 71, m.embed_dim) and out["row_shard"] == (0, 37)
+    assert tuple(out["row_attentions"].shape[-2:]) == (71, 71)
+    assert O.rel_err(out["representations"][3].cpu(), ref["representations"][3].cpu()) < 2e-3
+    assert O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"].cpu()) < 2e-3
+    if fused:
+        host = ShardedHostOutput(3, m.num_attention_heads, 71, m.embed_dim, start=1)
+        out2 = sharded_forward(m, tokens, fused=True, host_out=host, gather_maps=False)
+        assert out2["row_attentions_range"] == (0, 71) and tuple(out2["row_attentions_rows"].shape[-2:]) == (71, 71)
+        want = ref["row_attentions"][0, :, :, 1:, 1:].reshape(-1, 70, 70).cpu()
+        assert O.rel_err(host.atp.clone(), want) < 2e-3
+        assert O.rel_err(host.emb, ref["representations"][3][0, 0, 1:].cpu()) < 2e-3
+        host.close()
+
+
+def _worker(rank, world, port, precision, q, shape=(64, 96)):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -88,17 +118,24 @@ def _worker(rank, world, port, precision, q):
         import rnamsm_b200 as pkg
         from rnamsm_b200.sharded import sharded_forward
         m = _model(pkg, 3, precision, f"cuda:{rank}")
-        tokens = O.make_tokens(64, 96, 4, pad_cols=2, pad_rows=2).to(f"cuda:{rank}")
+        tokens = O.make_tokens(shape[0], shape[1], 4, pad_cols=2, pad_rows=2).to(f"cuda:{rank}")
         ref = m(tokens, repr_layers=[3], need_head_weights=True, want_logits=False)
+        if shape[0] % world or shape[1] % (16 * world):
+            # padded inside: what is computed AT <pad> positions differs (and is read by nobody); compare the real tokens
+            keep = tokens.ne(m.vocab.pad_idx).unsqueeze(-1).float()
+            ref["representations"][3] = ref["representations"][3] * keep
+        else:
+            keep = None
+        mask = (lambda rep, r0=0, r1=None: rep if keep is None else rep * keep[:, r0:r1])
         out = sharded_forward(m, tokens, gather_rows=True)
         torch.cuda.synchronize()
-        errs = [O.rel_err(out["representations"][3].cpu(), ref["representations"][3].cpu()),
+        errs = [O.rel_err(mask(out["representations"][3]).cpu(), ref["representations"][3].cpu()),
                 O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"].cpu())]
         if precision == "fp16":                    # fused peer-memory schedule: row shard + full maps on every rank
             fo = sharded_forward(m, tokens, fused=True)
             torch.cuda.synchronize()
             r0, r1 = fo["row_shard"]
-            errs.append(O.rel_err(fo["representations"][3].cpu(), ref["representations"][3][:, r0:r1].cpu()))
+            errs.append(O.rel_err(mask(fo["representations"][3], r0, r1).cpu(), ref["representations"][3][:, r0:r1].cpu()))
             errs.append(O.rel_err(fo["row_attentions"].cpu(), ref["row_attentions"].cpu()))
             # host outputs: every rank DMAs the map rows it owns into the shared host buffer; emb on rank 0
             from rnamsm_b200.sharded import ShardedHostOutput
@@ -109,10 +146,11 @@ def _worker(rank, world, port, precision, q):
             assert fo2["row_attentions_rows"].shape[2] == i1 - i0
             L_ = tokens.shape[-1] - 1
             want_atp = ref["row_attentions"][0, :, :, 1:, 1:].reshape(-1, L_, L_).cpu()
-            errs.append(O.rel_err(fo2["representations"][3].cpu(), ref["representations"][3][:, r0:r1].cpu()))
+            errs.append(O.rel_err(mask(fo2["representations"][3], r0, r1).cpu(), ref["representations"][3][:, r0:r1].cpu()))
             errs.append(O.rel_err(host.atp.clone(), want_atp))       # complete on EVERY rank (shared memory)
             if rank == 0:
-                errs.append(O.rel_err(host.emb, ref["representations"][3][0, 0, 1:].cpu()))
+                emb = host.emb if keep is None else host.emb * keep[0, 0, 1:].cpu()
+                errs.append(O.rel_err(emb, ref["representations"][3][0, 0, 1:].cpu()))
                 errs.append(0.0)
             host.close()
         q.put((rank, max(errs[0::2]), max(errs[1::2])))
@@ -120,14 +158,15 @@ def _worker(rank, world, port, precision, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("shape", [(64, 96), (63, 91)], ids=["even", "uneven"])
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
-def test_world2_nccl_matches_single_gpu(precision):
+def test_world2_nccl_matches_single_gpu(precision, shape):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29710 + (os.getpid() % 200)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, precision, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, precision, q, shape)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(2)]

@@ -103,16 +103,27 @@ def _worker(rank, world, port, case, q):
         out = fwd.forward(tokens, need_head_weights=True, gather_rows=True)
         ref = O.forward(O.to_dtype(sd, torch.float64), tokens, repr_layers=[LAYERS], need_head_weights=True,
                         num_layers=LAYERS, want_logits=False)
-        e_rep = O.rel_err(out["representations"][LAYERS], ref["representations"][LAYERS])
+        got_rep, ref_rep = out["representations"][LAYERS], ref["representations"][LAYERS]
+        if R % world or C % world:
+            # internal <pad> rows change what the column attention computes AT <pad> positions (all keys masked: uniform
+            # over 6 rows instead of 5) -- values nobody reads; every real token must agree
+            keep = tokens.ne(O.PAD_IDX).unsqueeze(-1).to(ref_rep.dtype)
+            got_rep, ref_rep = got_rep * keep, ref_rep * keep
+        e_rep = O.rel_err(got_rep, ref_rep)
         e_att = O.rel_err(out["row_attentions"], ref["row_attentions"])
-        plan = ShardPlan(R, C, world, rank)
-        ok_plan = out["row_shard"] == (plan.r0, plan.r0 + plan.Rn) and plan.rows(rank).start == rank * (R // world)
+        Rp, Cp = -(-R // world) * world, -(-C // world) * world          # uneven shapes are padded inside forward()
+        plan = ShardPlan(Rp, Cp, world, rank)
+        valid = max(0, min(plan.Rn, R - plan.r0))
+        ok_plan = out["row_shard"] == (plan.r0, plan.r0 + valid) and plan.rows(rank).start == rank * (Rp // world)
+        ok_plan = ok_plan and tuple(out["representations"][LAYERS].shape[1:3]) == (R, C) \
+            and tuple(out["row_attentions"].shape[-2:]) == (C, C)
         q.put((rank, e_rep, e_att, ok_plan))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", [(8, 10, 0, 0), (6, 12, 3, 2)], ids=["nopad", "pad"])
+@pytest.mark.parametrize("case", [(8, 10, 0, 0), (6, 12, 3, 2), (7, 9, 0, 0), (5, 11, 2, 1)],
+                         ids=["nopad", "pad", "uneven", "uneven_pad"])
 def test_sharded_schedule_world2_gloo(case):
     world = 2
     ctx = mp.get_context("spawn")
