@@ -423,7 +423,20 @@ int row_attn_short_chunks(int R, int C, int H) {
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
   if (!enabled || C > kMaxC || C < 1 || R < 1 || H < 1) return 0;
-  const int sms = num_sms_dev();
+  // CTAs that can be co-resident (one per SM unless the device is partitioned or shares its shared memory): resolved once;
+  // if the kernel cannot be resident at all the three-kernel chain stays in use
+  static int resident = -1;
+  if (resident < 0) {
+    int per_sm = 0;
+    cudaFuncSetAttribute(row_attn_short_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(row_attn_short_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, row_attn_short_kernel<true>, kThreads, kSmem) != cudaSuccess) {
+      per_sm = 0;
+    }
+    cudaGetLastError();     // (no device, as in the CPU-only build container: the chain stays selected, nothing is launched)
+    resident = std::max(0, per_sm) * num_sms_dev();
+  }
+  const int sms = std::min(num_sms_dev(), resident);
   if (H > sms) return 0;
   const int want = std::min(R, sms / H);
   const int rpc = ceil_div(R, want);
@@ -433,7 +446,7 @@ int row_attn_short_chunks(int R, int C, int H) {
 int launch_row_attn_short_16(const void* qkv, int R, int C, int H, int fp16, float* partial, int n_chunks, const uint8_t* key_pad,
                              float logit_scale, float* map, void* probs_lp, int ldp, void* ctx, cudaStream_t st) {
   RNAMSM_REQUIRE(C >= 1 && C <= kMaxC, "row_attn_short: C=%d outside [1, %d]", C, kMaxC);
-  RNAMSM_REQUIRE(n_chunks >= 1 && n_chunks <= R && (long long)H * n_chunks <= num_sms_dev(),
+  RNAMSM_REQUIRE(n_chunks >= 1 && n_chunks <= R && (long long)H * n_chunks <= num_sms_dev() && row_attn_short_chunks(R, C, H) > 0,
                  "row_attn_short: %d heads x %d chunks do not fit the device (R=%d)", H, n_chunks, R);
   RNAMSM_REQUIRE(ldp % 8 == 0 && ldp >= C, "row_attn_short: ldp=%d must be a multiple of 8 and >= C=%d", ldp, C);
   RNAMSM_REQUIRE(partial && map && probs_lp && ctx, "row_attn_short: null buffer");
