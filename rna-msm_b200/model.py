@@ -106,6 +106,31 @@ class MSATransformer(nn.Module, _PrecisionMixin):
             if isinstance(module, (RowSelfAttention, ColumnSelfAttention)):
                 module.max_tokens_per_msa = value
 
+    @torch.no_grad()
+    def check_fp16_range(self, tokens, fallback: Optional[str] = "bf16") -> Dict[str, object]:
+        """Guard for weights never validated in fp16 (the trained RNA-MSM checkpoint is not available offline,
+        RNA_MSM_Inference.py:133-135): runs ONE forward of ``tokens`` under the library's range watch, which scans every
+        16-bit activation the forward writes (LayerNorm outputs, q|k|v, attention contexts, the post-GELU hidden) for the
+        type's largest finite value -- where the fp16 kernels clamp (``cvt.rn.satfinite``).  Returns
+        ``{"saturated": n, "max_abs": m, "precision": p}`` (n, m of the fp16 pass); if anything saturated and ``fallback``
+        is given, the model is switched to that precision (default ``'bf16'``: fp32's exponent range; its tied row block
+        is still fp16, so the watch runs once more and ``'bf16_pure'`` is selected if that block is what overflowed).
+        A debugging pass: it adds one scan per activation tensor, so call it once per checkpoint / input family."""
+        if self.precision not in ("fp16",):
+            return {"saturated": 0, "max_abs": float("nan"), "precision": self.precision}
+
+        def watched():
+            with L.RangeWatch() as w:
+                self(tokens, repr_layers=[self.num_layers], need_head_weights=True, want_logits=False)
+            return w
+
+        w = watched()
+        if w.saturated and fallback is not None:
+            self.set_precision(fallback)
+            if fallback == "bf16" and watched().saturated:
+                self.set_precision("bf16_pure")
+        return {"saturated": w.saturated, "max_abs": w.max_abs, "precision": self.precision}
+
     def get_sequence_attention(self, tokens):
         return self(tokens.to(device=self.device), need_head_weights=True)["row_attentions"]
 

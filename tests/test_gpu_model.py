@@ -280,6 +280,30 @@ def test_fp16_range_stress_and_watch(pkg):
     assert argmax_agreement(out["row_attentions"].cpu(), ref["row_attentions"]) >= 0.98   # ... and it stays local
 
 
+def test_check_fp16_range_falls_back_to_bf16(pkg):
+    """MSATransformer.check_fp16_range: in-range weights keep fp16; weights that drive the FFN hidden past 65504 are
+    detected on the first forward and the model switches to bf16, whose result is then within the bf16 envelope."""
+    tokens = O.make_tokens(24, 40, 3)
+    vocab = pkg.Vocab(pkg.Alphabet())
+    for scale, want in ((1.0, "fp16"), (28000.0, "bf16")):
+        sd = O.make_weights(5, num_layers=2, sharpen=2.0)
+        for l in range(2):
+            sd[f"layers.{l}.feed_forward_layer.layer.fc1.weight"] *= scale
+            sd[f"layers.{l}.feed_forward_layer.layer.fc2.weight"] /= scale
+        model = pkg.MSATransformer(vocab, num_layers=2, precision="fp16")
+        model.load_state_dict(sd, strict=True)
+        model = model.eval().cuda()
+        rep = model.check_fp16_range(tokens.cuda())
+        print(f"[range guard] scale {scale:g}: {rep}")
+        assert rep["precision"] == want == model.precision and (rep["saturated"] > 0) == (want == "bf16")
+        assert all(m.precision == want for m in model.modules() if hasattr(m, "precision"))
+        out = model(tokens.cuda(), repr_layers=[2], need_head_weights=True, want_logits=False)
+        ref = O.forward(sd, tokens, repr_layers=[2], need_head_weights=True, num_layers=2, want_logits=False)
+        assert torch.isfinite(out["representations"][2]).all()
+        assert O.rel_err(out["row_attentions"].cpu(), ref["row_attentions"]) < BF16_TOL_DEEP_SHARP
+    assert pkg.MSATransformer(vocab, num_layers=1, precision="fp32").eval().cuda().check_fp16_range(tokens.cuda())["saturated"] == 0
+
+
 def test_bf16_mode_beats_the_reference_cast_to_bf16(pkg, golden_dir):
     """Why the 'bf16' mode is gated at 6e-2 and not at the 2e-2 the fp16 path meets: on BASELINE config 1 bf16 WEIGHTS
     alone (every activation exact) already put 4.4e-2 on the maps, and the reference itself cast to bf16 9.3e-2
