@@ -64,6 +64,16 @@ constexpr int kLnMaxVec = 8;                     // N <= 8 * 128 features per ro
 constexpr int kLnSlots = 4;                      // tiles the epilogue may run ahead of the LayerNorm warps
 constexpr int EPI_BUF_BYTES = 32 * 128;          // one 32-row x 128 B staging box per epilogue warp
 constexpr int kSmemBytes = kStagesDefault * STAGE_BYTES + kEpiWarps * EPI_BUF_BYTES + 256 + 1024;
+// kWide (the fc1 + GELU instance): 16 epilogue warps, each owning 32 rows x 64 columns of the accumulator instead of
+// 32 x 128, and a 5-stage operand ring so that their 16 staging boxes fit.  The GELU epilogue is ~2200 instructions per
+// warp and tile with little parallelism inside a warp (ncu: issue slots 49 % busy at two epilogue warps per scheduler);
+// at 8 warps it takes about as long as the 12 k-blocks of the tile's MMAs and the tensor pipe waits for its accumulator
+// buffer (fc1 1181 TF/s vs 1332 with the bias-only epilogue, tools/epi_cost_bench.py).
+constexpr int kEpiWarpsWide = 16;
+constexpr int kThreadsWide = 32 * (kFirstEpiWarp + kEpiWarpsWide);
+constexpr int kStagesWide = 5;
+static_assert(kStagesWide * STAGE_BYTES + kEpiWarpsWide * EPI_BUF_BYTES == kStagesDefault * STAGE_BYTES + kEpiWarps * EPI_BUF_BYTES,
+              "the wide-epilogue variant uses the same shared-memory footprint");
 
 enum { V_DENSE = 0, V_TIED = 1, V_AV = 2 };
 
@@ -201,8 +211,8 @@ __device__ __forceinline__ void stage_row(uint8_t* buf, int lane, const uint32_t
 
 // kBN = accumulator columns of the pair tile (256; 128 / 64 for the tied logits of short alignments, where a
 // 256-wide tile would be mostly padding): each CTA stages kBN / 2 rows of B, TMEM holds 2 x kBN columns.
-template <int kVariant, int kBN, bool kLN = false, bool kTf32 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLN ? kThreadsLn : kThreads, 1)
+template <int kVariant, int kBN, bool kLN = false, bool kTf32 = false, bool kWide = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLN ? kThreadsLn : (kWide ? kThreadsWide : kThreads), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g,
                  const __grid_constant__ PeerMaps peers) {
@@ -210,7 +220,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // bytes per CTA per k-block: A + B tiles (16-bit: 64 elements of K per 128 B row); kTf32: hi and lo tiles of both
   // operands (fp32: 32 elements of K per 128 B row) in a shallower ring
   constexpr int STG = kTf32 ? 4 * A_BYTES : A_BYTES + HN * BLOCK_K * 2;
-  constexpr int kStages = kTf32 ? 3 : kStagesDefault;
+  constexpr int kStages = kTf32 ? 3 : (kWide ? kStagesWide : kStagesDefault);
+  constexpr int EPW = kWide ? kEpiWarpsWide : kEpiWarps;   // epilogue warps per CTA
+  constexpr int CW = kBN / (EPW / 4);                      // accumulator columns per epilogue warp (128; wide: 64)
+  static_assert(!kWide || (kVariant == V_DENSE && kBN == BLOCK_N && !kLN && !kTf32), "wide epilogue: the dense 16-bit variant only");
   constexpr int KB_ELEMS = kTf32 ? 32 : BLOCK_K;         // K elements per k-block
   static_assert(!kTf32 || (kVariant == V_DENSE && kBN == BLOCK_N && !kLN), "tf32 split: the dense 256-wide variant only");
   constexpr int TMC = 2 * kBN;                           // TMEM columns (power of two >= 32)
@@ -219,7 +232,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // window starts at the same offset in both CTAs, so the carve-up below is identical in the pair.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* epi_smem = smem + kStages * STG;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * EPI_BUF_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPW * EPI_BUF_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -247,7 +260,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);                // multicast tcgen05.commit
-      mbar_init(&tmem_empty[a], 2 * kEpiWarps);   // epilogue warps of both CTAs (leader's copy is used)
+      mbar_init(&tmem_empty[a], 2 * EPW);         // epilogue warps of both CTAs (leader's copy is used)
     }
     for (int a = 0; a < kLnSlots; ++a) {
       mbar_init(&ln_ready[a], kEpiWarps);         // this CTA's epilogue warps
@@ -347,10 +360,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= kFirstEpiWarp && warp < kFirstLnWarp) {
+  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + EPW) {
     // ================================ epilogue (both CTAs) ========================
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
-    const int half = (warp - kFirstEpiWarp) >> 2;    // accumulator columns [128*half, 128*half+128)
+    const int half = (warp - kFirstEpiWarp) >> 2;    // accumulator columns [CW*half, CW*half+CW)
     uint8_t* buf = epi_smem + (warp - kFirstEpiWarp) * EPI_BUF_BYTES;
     const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     int acc = 0;
@@ -366,7 +379,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const TileCoord t = decode_tile<kVariant, kBN>(g, tile);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + half * HN + ((uint32_t)(quad * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * BN + half * CW + ((uint32_t)(quad * 32) << 16);
       const int row0 = t.m0 + cta_rank * BLOCK_M + quad * 32;   // first logical row of this warp's box
       auto release_acc = [&]() {                     // every tcgen05.ld of this tile has completed
         tc_fence_before();
@@ -378,12 +391,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // fp32 partial logits, direct stores (C need not be a multiple of 4)
         const int i = row0 + lane;
 #pragma unroll 1
-        for (int c = 0; c < HN / 32; ++c) {
+        for (int c = 0; c < CW / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (c == HN / 32 - 1) release_acc();
-          const int j0 = t.n0 + half * HN + c * 32;
+          if (c == CW / 32 - 1) release_acc();
+          const int j0 = t.n0 + half * CW + c * 32;
           if (i >= g.C || j0 >= g.C) continue;
           float* dst = reinterpret_cast<float*>(g.out) + (((size_t)t.split * g.H + t.batch) * g.C + i) * g.C + j0;
           if ((g.C & 3) == 0 && j0 + 32 <= g.C) {
@@ -400,14 +413,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       } else if (kVariant == V_DENSE && g.epi_kind == RNAMSM_EPI_BIAS_RESIDUAL) {
         // out(fp32) += acc + bias: 32-column boxes, TMA reduce-add into the residual stream
 #pragma unroll 1
-        for (int c = 0; c < HN / 32; ++c) {
+        for (int c = 0; c < CW / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (c == HN / 32 - 1) release_acc();
-          const int n = t.n0 + half * HN + c * 32;
+          if (c == CW / 32 - 1) release_acc();
+          const int n = t.n0 + half * CW + c * 32;
           if (n >= g.N || row0 >= g.M) {
-            if (kLN && lane == 0) bulk_commit();       // an empty group: every tile commits exactly HN / 32 groups
+            if (kLN && lane == 0) bulk_commit();       // an empty group: every tile commits exactly CW / 32 groups
             continue;
           }
 #pragma unroll
@@ -441,20 +454,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if (kLN && lt > 0 && lane == 0) {
-          // all but this tile's HN / 32 groups are complete = the PREVIOUS tile's reduce-adds have been performed at
+          // all but this tile's CW / 32 groups are complete = the PREVIOUS tile's reduce-adds have been performed at
           // L2 (not merely read out of the staging buffer): tell the LayerNorm warps, one tile late and without stalling
-          bulk_wait_pending<HN / 32>();
+          bulk_wait_pending<CW / 32>();
           ln_signal(lt - 1);
         }
       } else if (kTf32) {
         // fp32 outputs (bias, q scale / row mask, exact erf-GELU as in the FFMA path): 32-column boxes, TMA store
 #pragma unroll 1
-        for (int c = 0; c < HN / 32; ++c) {
+        for (int c = 0; c < CW / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (c == HN / 32 - 1) release_acc();
-          const int n = t.n0 + half * HN + c * 32;
+          if (c == CW / 32 - 1) release_acc();
+          const int n = t.n0 + half * CW + c * 32;
           if (n >= g.N || row0 >= g.M) continue;
           float s = 1.f;
           if (g.epi_kind == RNAMSM_EPI_BIAS && n < g.q_cols) {   // q_cols is a multiple of 64
@@ -481,16 +494,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       } else {
         // 16-bit outputs: 64-column boxes (128 B rows), TMA store
 #pragma unroll 1
-        for (int c = 0; c < HN / 64; ++c) {
+        for (int c = 0; c < CW / 64; ++c) {
           uint32_t v0[32], v1[32];
           tmem_ld_32x32(taddr + c * 64, v0);
           tmem_ld_32x32(taddr + c * 64 + 32, v1);
           tmem_ld_wait();
-          if (c == HN / 64 - 1) release_acc();
+          if (c == CW / 64 - 1) release_acc();
           uint32_t w[32];
           int c0, c1, c2;
           if (kVariant == V_DENSE) {
-            const int n = t.n0 + half * HN + c * 64;
+            const int n = t.n0 + half * CW + c * 64;
             if (n >= g.N || row0 >= g.M) continue;
             float s = 1.f;
             if (g.epi_kind == RNAMSM_EPI_BIAS && n < g.q_cols) {   // q_cols is a multiple of 64
@@ -678,12 +691,12 @@ static void ensure_max_pairs() {
   g_max_pairs = std::max(1, std::min(n, num_sms() / 2));
 }
 
-template <int kVariant, int kBN = BLOCK_N, bool kLN = false, bool kTf32 = false>
+template <int kVariant, int kBN = BLOCK_N, bool kLN = false, bool kTf32 = false, bool kWide = false>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g,
                    int prof_class, cudaStream_t st, const PeerMaps* peers = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
-    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant, kBN, kLN, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RNAMSM_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kVariant, kBN, kLN, kTf32, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes));
     attr_set = true;
   }
@@ -693,8 +706,9 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int pairs = (int)std::min<long long>(total, g_max_pairs);
   ProfScope prof(prof_class, st);
   static const PeerMaps no_peers{};
-  RNAMSM_CHECK_CUDA(launch_pdl(umma_gemm_kernel<kVariant, kBN, kLN, kTf32>, dim3(2 * pairs), dim3(kLN ? kThreadsLn : kThreads),
-                               kSmemBytes, st, ta, tb, to, g, peers ? *peers : no_peers));
+  RNAMSM_CHECK_CUDA(launch_pdl(umma_gemm_kernel<kVariant, kBN, kLN, kTf32, kWide>, dim3(2 * pairs),
+                               dim3(kLN ? kThreadsLn : (kWide ? kThreadsWide : kThreads)), kSmemBytes, st, ta, tb, to, g,
+                               peers ? *peers : no_peers));
   count_launch();
   RNAMSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -760,6 +774,10 @@ int launch_linear_16(const void* x, const void* W, long long M, int N, int K, in
     }
     return launch_variant<V_DENSE, BLOCK_N, true>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
   }
+  static int wide = -1;                      // RNAMSM_GELU_WIDE=0: the 8-warp epilogue for the GELU instance too (A/B runs)
+  if (wide < 0) { const char* e = getenv("RNAMSM_GELU_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+  if (epi.kind == RNAMSM_EPI_BIAS_GELU && wide)
+    return launch_variant<V_DENSE, BLOCK_N, false, false, true>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
   return launch_variant<V_DENSE>(ta, tb, to, g, linear_class(epi.kind, N, K), st);
 }
 
