@@ -112,7 +112,11 @@ def class_flops(R, C):
     """flops_breakdown keyed by the library's timing classes: short alignments (C <= 128) run tied logits + softmax + AV
     as ONE launch (row_attn_short.cu), whose class carries both terms."""
     fl = flops_breakdown(R, C)
-    fl["row_attn_short"] = fl["row_logits"] + fl["row_av"]
+    if C <= 128:            # the one-launch path takes these shapes (16-bit precisions)
+        fl["row_attn_short"] = fl["row_logits"] + fl["row_av"]
+        fl["row_logits"] = fl["row_av"] = 0.0
+    else:
+        fl["row_attn_short"] = 0.0
     return fl
 
 
@@ -384,8 +388,9 @@ def run_secondary(args, pkg, _lib, world, rank, peaks):
             res["class_time_share"] = {k: round(v[0] / tot, 4) for k, v in prof.items() if v[1]}
             t_short = prof.get("row_attn_short", (0.0, 0))[0]   # one launch does logits + softmax + AV when C <= 128
             t_tied = prof["row_logits"][0] + prof["row_av"][0] + t_short
-            tied = (fl["row_logits"] + fl["row_av"]) * n_steps / (t_tied * 1e-3) / 1e12
-            tied_sm = (fl["row_logits"] + fl["row_av"]) * n_steps / ((t_tied + prof["row_softmax"][0]) * 1e-3) / 1e12
+            fl_tied = fl["row_logits"] + fl["row_av"] + fl["row_attn_short"]
+            tied = fl_tied * n_steps / (t_tied * 1e-3) / 1e12
+            tied_sm = fl_tied * n_steps / ((t_tied + prof["row_softmax"][0]) * 1e-3) / 1e12
             res["tied_row_attention"] = {
                 "tflops": round(tied, 1), "frac_of_bf16_sustained": round(tied / peaks["bf16_sustained"], 4),
                 "frac_of_bf16_burst": round(tied / peaks["bf16_burst"], 4),
