@@ -514,6 +514,11 @@ class FusedShardedForward:
         D, H = self.m.embed_dim, self.m.num_attention_heads
         Rn, Cn = R // n, C // n
         splits = L.lib.rnamsm_row_attn_splits(Rn, C, H, self.row_code)
+        # Every split is one more [H, C/n, C] fp32 slab that each rank pulls from each peer over NVLink in the P2P
+        # softmax: at 1024 x 1024 on 8 GPUs the wave-efficient 3 splits made that 132 MB per rank and layer (190 us at the
+        # measured 700 GB/s) to save ~10 % of a 180 us GEMM.  Keep the pull under ~32 MB; short alignments keep their splits.
+        per_split = (n - 1) * H * Cn * C * 4
+        splits = max(1, min(splits, (32 << 20) // max(1, per_split))) if n > 1 else splits
         ldp = (C + 7) // 8 * 8
         b = {
             "x": PeerBuffer(Rn * C * D * 4, self.group),
