@@ -30,6 +30,9 @@
 // softmax rows in phase 2.
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/rnamsm_b200.h"
 #include "common.cuh"
 #include "launch.h"
@@ -359,16 +362,27 @@ row_attn_short_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_co
   if (threadIdx.x == 0 && atomicAdd(a.sync, 1u) == 3u * gridDim.x - 1u) atomicExch(a.sync, 0u);
 }
 
+// Grid-barrier counters: a ring of 64 per device (128 B apart), one per launch in round-robin order, so launches of this
+// kernel that overlap in time (two streams, two model instances) never share a counter; each is zero between uses
+// (the last CTA of a launch resets its own).
 unsigned* sync_counter() {
+  constexpr int kRing = 64, kStride = 32;                    // 32 x 4 B = 128 B
   static unsigned* ptr[64] = {};
+  static std::atomic<unsigned> next[64];
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
   if (ptr[dev] == nullptr) {
-    if (cudaMalloc(&ptr[dev], 256) != cudaSuccess) return nullptr;
-    cudaMemset(ptr[dev], 0, 256);
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (ptr[dev] == nullptr) {
+      unsigned* p = nullptr;
+      if (cudaMalloc(&p, kRing * kStride * sizeof(unsigned)) != cudaSuccess) return nullptr;
+      cudaMemset(p, 0, kRing * kStride * sizeof(unsigned));
+      ptr[dev] = p;
+    }
   }
-  return ptr[dev];
+  return ptr[dev] + (size_t)(next[dev].fetch_add(1, std::memory_order_relaxed) % kRing) * kStride;
 }
 
 int num_sms_dev() {

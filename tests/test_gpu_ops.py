@@ -308,6 +308,39 @@ def test_row_attention_short(L, R, C, with_pad, code):
     assert rel(ctx, ctx2.double().cpu()) < 1e-3
 
 
+def test_row_attention_short_on_two_streams(L):
+    """Launches of the one-launch kernel that overlap in time (two streams) take different barrier counters from the
+    per-device ring: both streams must reproduce the result of a lone launch, bit for bit."""
+    R, C, code = 96, 36, 2
+    dt = L.torch_dtype(code)
+    ldp = (C + 7) // 8 * 8
+    chunks = L.lib.rnamsm_row_attn_short_chunks(R, C, H)
+    sets = []
+    for seed in (41, 42):
+        qkv, _ = make_qkv(R, C, seed, code, L, 0.4)
+        sets.append(dict(qkv=qkv, partial=torch.empty(chunks, H, C, C, device="cuda"), pmap=torch.empty(H, C, C, device="cuda"),
+                         plp=torch.empty(H, C, ldp, dtype=dt, device="cuda"), ctx=torch.empty(R * C, D, dtype=dt, device="cuda")))
+
+    def launch(b, stream):
+        L.check(L.lib.rnamsm_row_attn_short(L.ptr(b["qkv"]), R, C, H, code, None, 1.0 / math.sqrt(R), L.ptr(b["partial"]), chunks,
+                                            L.ptr(b["pmap"]), L.ptr(b["plp"]), ldp, L.ptr(b["ctx"]), stream))
+
+    want = []
+    for b in sets:
+        launch(b, L.stream_ptr())
+        torch.cuda.synchronize()
+        want.append((b["pmap"].clone(), b["ctx"].clone()))
+        b["pmap"].zero_(); b["ctx"].zero_()
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(40):
+        for b, st in zip(sets, streams):
+            launch(b, st.cuda_stream)
+    torch.cuda.synchronize()
+    for b, (pm, cx) in zip(sets, want):
+        assert torch.equal(b["pmap"], pm) and torch.equal(b["ctx"], cx)
+
+
 # ------------------------------------------------------------------------------------------ K7
 @pytest.mark.parametrize("R,C,with_pad", [(2, 5, False), (9, 7, True), (64, 3, False), (65, 4, True), (130, 6, True),
                                           (300, 2, False), (257, 3, True), (300, 7, True), (520, 13, False),
