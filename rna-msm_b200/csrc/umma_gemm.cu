@@ -223,7 +223,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   constexpr int kStages = kTf32 ? 3 : (kWide ? kStagesWide : kStagesDefault);
   constexpr int EPW = kWide ? kEpiWarpsWide : kEpiWarps;   // epilogue warps per CTA
   constexpr int CW = kBN / (EPW / 4);                      // accumulator columns per epilogue warp (128; wide: 64)
-  static_assert(!kWide || (kVariant == V_DENSE && kBN == BLOCK_N && !kLN && !kTf32), "wide epilogue: the dense 16-bit variant only");
+  static_assert(!kWide || ((kVariant == V_DENSE || kVariant == V_AV) && kBN == BLOCK_N && !kLN && !kTf32),
+                "wide epilogue: the 16-bit-output variants only");
   constexpr int KB_ELEMS = kTf32 ? 32 : BLOCK_K;         // K elements per k-block
   static_assert(!kTf32 || (kVariant == V_DENSE && kBN == BLOCK_N && !kLN), "tf32 split: the dense 256-wide variant only");
   constexpr int TMC = 2 * kBN;                           // TMEM columns (power of two >= 32)
@@ -533,7 +534,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             c0 = n; c1 = row0; c2 = 0;
           } else {  // V_AV: columns = (MSA row r, 64 head dims); rows = query column i
-            const int r = t.n0 + half * 2 + c;
+            const int r = t.n0 + half * (CW / 64) + c;
             if (r >= g.R || row0 >= g.C) continue;
 #pragma unroll
             for (int k = 0; k < 32; k += 2) {
@@ -943,6 +944,11 @@ int launch_row_av_16(const void* probs, int ldp, const void* qkv, int R, int C, 
   g.R = R; g.C = C; g.H = H; g.M = C; g.N = R;
   g.fp16 = fp16;
   g.out = ctx; g.ld_out = H * 64;
+  // the A V tile has K = C: at C = 256 only four k-blocks of MMAs stand against a 256 x 256 16-bit epilogue, so the
+  // 16-warp epilogue (kWide, see above) is what bounds the tile less
+  static int wide = -1;
+  if (wide < 0) { const char* e = getenv("RNAMSM_AV_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+  if (wide) return launch_variant<V_AV, BLOCK_N, false, false, true>(ta, tb, to, g, KC_ROW_AV, st);
   return launch_variant<V_AV>(ta, tb, to, g, KC_ROW_AV, st);
 }
 
