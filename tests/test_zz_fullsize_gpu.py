@@ -140,6 +140,40 @@ def test_tied_row_attention_full_size(L, R, C):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("R,C", [(4096, 128), (1024, 100)], ids=["cfg4", "deep_ragged"])
+def test_tied_row_attention_one_launch_full_size(L, R, C):
+    """The one-launch kernel for <= 128 columns (rnamsm_row_attn_short) at BASELINE config 4's full shape and at a
+    width that is neither a multiple of 16 nor of 64: float64 logits of three heads (from q, k), its own softmax on
+    them, and the context of three (row, head) blocks."""
+    need_gb(24)
+    qkv = randn_f16((R * C, 3 * D), 21, 0.4)
+    chunks = L.lib.rnamsm_row_attn_short_chunks(R, C, H)
+    assert chunks >= 1
+    partial = torch.empty(chunks, H, C, C, device="cuda")
+    pmap = torch.empty(H, C, C, device="cuda")
+    ldp = (C + 7) // 8 * 8
+    plp = torch.empty(H, C, ldp, dtype=torch.float16, device="cuda")
+    ctx = torch.empty(R * C, D, dtype=torch.float16, device="cuda")
+    scale = 1.0 / (R ** 0.5)
+    L.check(L.lib.rnamsm_row_attn_short(L.ptr(qkv), R, C, H, F16, None, scale, L.ptr(partial), chunks, L.ptr(pmap), L.ptr(plp),
+                                        ldp, L.ptr(ctx), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(ctx).all())
+    heads = (0, 7, 11)
+    refs = {h: ref_tied_logits_head(qkv, R, C, h) for h in heads}
+    logits = partial.sum(0)
+    for h in heads:
+        assert rel(logits[h], refs[h]) < 1e-3, h
+        assert rel(pmap[h], (refs[h] * scale).softmax(-1)) < 1e-2, h
+    assert float((pmap.sum(-1) - 1).abs().max()) < 1e-5 and float(pmap.min()) >= 0.0
+    assert rel(pmap, (partial.double().sum(0) * scale).softmax(-1)) < 5e-5
+    assert rel(plp[..., :C], pmap) < 5e-3 and float(plp[..., C:].float().abs().sum()) == 0.0
+    got = ctx.view(R, C, D)
+    for r, h in ((0, 0), (R // 2 + 1, 7), (R - 1, 11)):
+        assert rel(got[r, :, h * HD:(h + 1) * HD], ref_av_block(plp[h], qkv, R, C, r, h)) < 2e-3, (r, h)
+
+
+@pytest.mark.gpu
 def test_dense_linear_and_layernorm_full_size(L):
     """K2 / K3 / K8 over the 1 048 576 tokens of cfg5 (outputs of 6.4 GB: offsets beyond 2^32 bytes): LayerNorm with the
     token transpose, fc1 + GELU, fc2 + residual, checked on sampled tokens from the first, middle and last tiles."""
