@@ -59,7 +59,9 @@ def extract_features_streamed(model: MSATransformer, tokens: torch.Tensor, atp_h
         if side is None:
             side = model._copy_stream = torch.cuda.Stream()
         tok = tokens.to(dev, non_blocking=True).long().contiguous()
-        has_pad, _ = model.check_tokens(tok)          # same limits and exceptions as forward()
+        # same limits and exceptions as forward(); host tokens are checked on the host, so the first kernel does not
+        # wait for a device -> host round trip of the "any padding?" flag (model.py:347)
+        has_pad, _ = model.check_tokens(tokens if tokens.device.type == "cpu" else tok)
         x = torch.empty((R * Cc, D), dtype=torch.float32, device=dev)
         pad = torch.empty(R * Cc, dtype=torch.uint8, device=dev)
         maps = torch.empty((N, H, Cc, Cc), dtype=torch.float32, device=dev)
@@ -81,10 +83,17 @@ def extract_features_streamed(model: MSATransformer, tokens: torch.Tensor, atp_h
                     "layer_forward")
             ev = torch.cuda.Event()
             ev.record(main)
-            with torch.cuda.stream(side):
-                side.wait_event(ev)
-                atp_host[l * H:(l + 1) * H].copy_(maps[l, :, start:start + Ls, start:start + Ls], non_blocking=True)
-        L.check(L.lib.rnamsm_layernorm(L.ptr(x), m.ln_after_w, m.ln_after_b, L.ptr(x), L.F32, R * Cc, D, m.ln_eps, 0, 0, st),
+            side.wait_event(ev)
+            if atp_host.is_contiguous() and atp_host.dtype == torch.float32 and tuple(atp_host.shape[-2:]) == (Ls, Ls):
+                # one pitched DMA per layer straight into the *_atp.npy layout: no staging kernel on the GPU
+                L.check(L.lib.rnamsm_copy_map_rows_d2h(L.ptr(maps[l]), H, Cc, 0, Cc, start, Ls, atp_host[l * H].data_ptr(),
+                                                       side.cuda_stream), "copy_map_rows_d2h")
+            else:
+                with torch.cuda.stream(side):
+                    atp_host[l * H:(l + 1) * H].copy_(maps[l, :, start:start + Ls, start:start + Ls], non_blocking=True)
+        # *_emb.npy is MSA row 0 of the final representation (RNA_MSM_Inference.py:159-166): the final LayerNorm is
+        # token-local, so only that row's C tokens are normalised here (forward() returns all rows and normalises all)
+        L.check(L.lib.rnamsm_layernorm(L.ptr(x), m.ln_after_w, m.ln_after_b, L.ptr(x), L.F32, Cc, D, m.ln_eps, 0, 0, st),
                 "layernorm")
         emb_host.copy_(x.view(R, Cc, D)[0, start:start + Ls], non_blocking=True)
         maps.record_stream(side)
