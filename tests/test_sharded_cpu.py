@@ -152,3 +152,16 @@ def test_shard_plan_and_traffic_model():
         ShardPlan(1001, 1024, 8, 0)
     with pytest.raises(ValueError):
         ShardPlan(8, 8, 2, 2)
+
+
+def test_pad_to_shards_shapes_and_content():
+    """Uneven shapes are padded with <pad> up to world | R and world * col_multiple | C; even shapes pass through."""
+    from rnamsm_b200.sharded import pad_to_shards
+    tok = O.make_tokens(7, 9, 1)
+    assert pad_to_shards(tok, 1, 1, O.PAD_IDX) is tok
+    out = pad_to_shards(tok, 2, 1, O.PAD_IDX)
+    assert tuple(out.shape) == (1, 8, 10) and torch.equal(out[:, :7, :9], tok)
+    assert bool((out[:, 7:, :] == O.PAD_IDX).all()) and bool((out[:, :, 9:] == O.PAD_IDX).all())
+    assert tuple(pad_to_shards(tok, 8, 16, O.PAD_IDX).shape) == (1, 8, 128)
+    even = O.make_tokens(8, 32, 1)
+    assert pad_to_shards(even, 2, 16, O.PAD_IDX) is even
